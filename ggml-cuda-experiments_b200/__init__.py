@@ -1,0 +1,13 @@
+"""b200fa — B200-native (sm_100a) flash attention behind the launcher interface of
+FSSRepo/ggml-cuda-experiments (flash_attn_ext_f16 / flash_attn_row + fa_reduce).
+
+The product is the C-ABI library built from csrc/ (include/b200fa.h).  This package is the thin host
+side used by tests and bench.py: ctypes bindings over that ABI, taking torch tensors only as owners of
+device memory.  There is no CPU or PyTorch compute path: importing works anywhere, but every call
+raises if libb200fa.so is missing or no sm_100 device is present.
+"""
+from .api import (  # noqa: F401
+    FLAG_CAUSAL, FLAG_NO_TCGEN05, TYPE_F16, TYPE_F32, TYPE_Q8_0, B200FAError, Workspace, dequantize_q8_0,
+    flash_attn_ext, flash_attn_ext_raw, flash_attn_partial, last_dispatch, last_launch_count, lib, merge_partials,
+    quantize_q8_0, workspace_size)
+from .build import build  # noqa: F401

@@ -1,0 +1,198 @@
+"""ctypes bindings over include/b200fa.h.
+
+`flash_attn_ext_raw` is the ABI call itself: pointers, ne/nb, flags, workspace, stream — the argument
+list of the reference kernel (flash-llama.h:6-32).  `flash_attn_ext` derives ne/nb from torch tensors
+laid out the ggml way (torch shape [ne3][ne2][ne1][ne0], any strides) and owns nothing but the call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB, build
+
+TYPE_F32, TYPE_F16, TYPE_Q8_0 = 0, 1, 8
+FLAG_CAUSAL, FLAG_NO_TCGEN05 = 1, 2
+Q8_BLOCK_BYTES, Q8_BLOCK_ELEMS = 34, 32
+
+_lib = None
+
+
+class B200FAError(RuntimeError):
+    def __init__(self, status: int, what: str):
+        self.status = status
+        super().__init__(f"{what}: {lib().b200fa_status_string(status).decode()} ({status})")
+
+
+def lib() -> C.CDLL:
+    """Load libb200fa.so (building it if the sources are newer).  Fails loudly if it cannot be had."""
+    global _lib
+    if _lib is None:
+        path = LIB if os.path.exists(LIB) and os.environ.get("B200FA_NO_REBUILD") else build()
+        l = C.CDLL(path)
+        i64, vp = C.c_int64, C.c_void_p
+        l.b200fa_status_string.restype = C.c_char_p
+        l.b200fa_status_string.argtypes = [C.c_int]
+        l.b200fa_last_dispatch.restype = C.c_char_p
+        l.b200fa_last_launch_count.restype = C.c_int
+        l.b200fa_version.restype = C.c_int
+        l.b200fa_flash_attn_ext.restype = C.c_int
+        l.b200fa_flash_attn_ext.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 3 + [i64] * 23 + [C.c_uint32, vp, C.c_size_t, vp]
+        l.b200fa_flash_attn_partial.restype = C.c_int
+        l.b200fa_flash_attn_partial.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 2 + [i64] * 21 + [C.c_uint32, vp, C.c_size_t, vp]
+        l.b200fa_workspace_size.restype = C.c_size_t
+        l.b200fa_workspace_size.argtypes = [C.c_int, C.c_int] + [i64] * 7 + [C.c_uint32]
+        l.b200fa_merge_partials.restype = C.c_int
+        l.b200fa_merge_partials.argtypes = [vp, C.c_int, i64, i64, vp, C.c_int, vp]
+        l.b200fa_quantize_q8_0.restype = C.c_int
+        l.b200fa_quantize_q8_0.argtypes = [vp, C.c_int, vp, i64, vp]
+        l.b200fa_dequantize_q8_0.restype = C.c_int
+        l.b200fa_dequantize_q8_0.argtypes = [vp, vp, i64, vp]
+        _lib = l
+    return _lib
+
+
+def last_dispatch() -> str:
+    return lib().b200fa_last_dispatch().decode()
+
+
+def last_launch_count() -> int:
+    return lib().b200fa_last_launch_count()
+
+
+def _stream_ptr(stream=None) -> int:
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def _ne_nb(t, type_: int):
+    """torch tensor [ne3][ne2][ne1][ne0] -> (ne, nb) ggml style; q8_0 tensors are uint8 [..., row_bytes]."""
+    shape = (1,) * (4 - t.dim()) + tuple(t.shape)
+    es = t.element_size()
+    strides = tuple(s * es for s in t.stride())
+    strides = ((strides[0] * t.shape[0],) * (4 - t.dim()) + strides) if t.dim() < 4 else strides
+    ne = tuple(reversed(shape)); nb = tuple(reversed(strides))
+    if type_ == TYPE_Q8_0:
+        ne = (ne[0] // Q8_BLOCK_BYTES * Q8_BLOCK_ELEMS,) + ne[1:]
+        nb = (Q8_BLOCK_BYTES,) + nb[1:]
+    return ne, nb
+
+
+def _type_of(t, explicit=None) -> int:
+    import torch
+    if explicit is not None:
+        return explicit
+    return {torch.float32: TYPE_F32, torch.float16: TYPE_F16, torch.uint8: TYPE_Q8_0}[t.dtype]
+
+
+def workspace_size(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, flags=0) -> int:
+    return lib().b200fa_workspace_size(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, flags)
+
+
+class Workspace:
+    """Caller-owned scratch (the reference cudaMallocs its own per call, flash-matrix.cu:223-224)."""
+
+    def __init__(self, nbytes: int, device=None):
+        import torch
+        self.nbytes = max(int(nbytes), 256)
+        self.buf = torch.empty(self.nbytes + 256, dtype=torch.uint8, device=device or "cuda")
+        self.ptr = (self.buf.data_ptr() + 255) // 256 * 256
+
+
+def flash_attn_ext_raw(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb,
+                       flags, ws_ptr, ws_bytes, stream_ptr) -> int:
+    """The ABI call.  q,k,v,mask,dst are device addresses (ints); returns the status code."""
+    return lib().b200fa_flash_attn_ext(
+        q, k, v, mask, dst, scale, q_type, kv_type, dst_type, *q_ne, *k_ne, ne31, nb31,
+        q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3],
+        q_ne[0], q_ne[2], q_ne[1], q_ne[3], flags, ws_ptr, ws_bytes, stream_ptr)
+
+
+def flash_attn_ext(q, k, v, mask=None, scale=None, dst=None, dst_dtype=None, flags=0, workspace: Workspace | None = None,
+                   stream=None, kv_type=None):
+    """dst[b][q][head][D] = softmax(scale·QKᵀ + mask)·V on the current CUDA device.
+
+    q  : [n_batch][n_head][n_q][D] view (any strides with 16-byte aligned rows), f32 or f16
+    k,v: [n_batch_kv][n_head_kv][n_kv][D] f16 views, or uint8 [..][n_kv][D/32*34] for q8_0
+    mask: f16 [>= n_q][n_kv] or None.  Returns dst (allocated if not given).
+    """
+    import torch
+    if not q.is_cuda:
+        raise B200FAError(-4, "b200fa has no CPU path")
+    qt, kt = _type_of(q), _type_of(k, kv_type)
+    q_ne, q_nb = _ne_nb(q, qt); k_ne, k_nb = _ne_nb(k, kt); _, v_nb = _ne_nb(v, kt)
+    D, n_q, n_head, n_b = q_ne
+    if scale is None:
+        scale = 1.0 / (D ** 0.5)
+    if dst is None:
+        dst = torch.empty((n_b, n_q, n_head, D), dtype=dst_dtype or torch.float32, device=q.device)
+    dt = _type_of(dst)
+    if workspace is None:
+        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+    m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
+    rc = flash_attn_ext_raw(q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, dt,
+                            q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb, flags, workspace.ptr, workspace.nbytes,
+                            _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_flash_attn_ext")
+    return dst
+
+
+def flash_attn_partial(q, k, v, mask=None, scale=None, kv_pos0=0, n_kv_total=None, flags=0,
+                       workspace: Workspace | None = None, stream=None, kv_type=None, out=None):
+    """Sequence-split building block: per-row (O~[D], m, l) over this device's KV slice -> f32 [rows][D+2]."""
+    import torch
+    qt, kt = _type_of(q), _type_of(k, kv_type)
+    q_ne, q_nb = _ne_nb(q, qt); k_ne, k_nb = _ne_nb(k, kt); _, v_nb = _ne_nb(v, kt)
+    D, n_q, n_head, n_b = q_ne
+    if scale is None:
+        scale = 1.0 / (D ** 0.5)
+    if n_kv_total is None:
+        n_kv_total = kv_pos0 + k_ne[1]
+    if out is None:
+        out = torch.empty((n_b * n_q * n_head, D + 2), dtype=torch.float32, device=q.device)
+    if workspace is None:
+        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+    m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
+    rc = lib().b200fa_flash_attn_partial(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, out.data_ptr(), scale, qt, kt, *q_ne, *k_ne, ne31, nb31,
+        q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
+        flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_flash_attn_partial")
+    return out
+
+
+def merge_partials(partials, dst=None, dst_dtype=None, stream=None):
+    """partials f32 [n_parts][rows][D+2] -> dst [rows][D]  (fa_reduce algebra, flash_row_float.h:415-472)."""
+    import torch
+    n_parts, rows, d2 = partials.shape
+    if dst is None:
+        dst = torch.empty((rows, d2 - 2), dtype=dst_dtype or torch.float32, device=partials.device)
+    rc = lib().b200fa_merge_partials(partials.data_ptr(), n_parts, rows, d2 - 2, dst.data_ptr(), _type_of(dst),
+                                     _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_merge_partials")
+    return dst
+
+
+def quantize_q8_0(x, stream=None):
+    """f32/f16 [..., D] (contiguous) -> uint8 [..., D/32*34] ggml q8_0 rows."""
+    import torch
+    x = x.contiguous()
+    out = torch.empty(x.shape[:-1] + (x.shape[-1] // Q8_BLOCK_ELEMS * Q8_BLOCK_BYTES,), dtype=torch.uint8, device=x.device)
+    rc = lib().b200fa_quantize_q8_0(x.data_ptr(), _type_of(x), out.data_ptr(), x.numel(), _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_quantize_q8_0")
+    return out
+
+
+def dequantize_q8_0(y, stream=None):
+    import torch
+    y = y.contiguous()
+    out = torch.empty(y.shape[:-1] + (y.shape[-1] // Q8_BLOCK_BYTES * Q8_BLOCK_ELEMS,), dtype=torch.float32, device=y.device)
+    rc = lib().b200fa_dequantize_q8_0(y.data_ptr(), out.data_ptr(), out.numel(), _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_dequantize_q8_0")
+    return out

@@ -1,0 +1,305 @@
+// b200fa_api.cu — the C ABI declared in include/b200fa.h: argument validation, kernel selection,
+// split-KV planning and launches.  No allocation, no synchronisation, no CPU compute path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "decode_mma.cuh"
+#include "prefill_tcgen05.cuh"
+#include "q8_0.cuh"
+
+using namespace b200fa;
+
+namespace {
+
+thread_local const char* g_last_dispatch = "none";
+thread_local int g_last_launches = 0;
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int cc_major = 0;
+    bool ok = false;
+};
+
+const DeviceInfo& device_info() {
+    static thread_local DeviceInfo cache[64];
+    static DeviceInfo none;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return none;
+    DeviceInfo& d = cache[dev];
+    if (!d.ok) {
+        if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return none;
+        if (cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return none;
+        d.ok = true;
+    }
+    return d;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Plan {
+    bool use_prefill = false;
+    int n_splits = 1;
+    int split_len = 0;
+    int n_groups = 1;
+    size_t part_bytes = 0;   // split-KV partials
+    size_t qf16_bytes = 0;   // f16 copy of an f32 Q (tcgen05 path)
+    size_t cls_bytes = 0;    // mask tile classes (tcgen05 path)
+    size_t total = 0;
+};
+
+Plan make_plan(int q_type, int kv_type, int64_t D, int64_t n_q, int64_t n_head, int64_t n_batch,
+               int64_t n_kv, int64_t n_head_kv, uint32_t flags, int sm_count, bool force_partial_out) {
+    Plan pl;
+    const int64_t gqa = n_head / n_head_kv;
+    const int64_t rows = n_q * gqa;
+    pl.use_prefill = !force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D == 128 &&
+                     kv_type == B200FA_TYPE_F16 && n_q >= 64;
+    if (pl.use_prefill) {
+        if (q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * D * 2), 256);
+        const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;
+        pl.cls_bytes = align_up((size_t)(qt * kt), 256);
+        pl.total = pl.qf16_bytes + pl.cls_bytes;
+        return pl;
+    }
+    pl.n_groups = (int)((rows + kRows - 1) / kRows);
+    const int64_t base = (int64_t)pl.n_groups * n_head_kv * n_batch;
+    int64_t target = (int64_t)sm_count * 12;  // ~3 resident CTAs per SM x 4 waves
+    if (const char* e = getenv("B200FA_TARGET_CTAS")) target = atoll(e);
+    int64_t want = (target + base - 1) / base;
+    const int64_t min_keys = 256;
+    int64_t max_splits = (n_kv + min_keys - 1) / min_keys;
+    if (max_splits < 1) max_splits = 1;
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    if (const char* e = getenv("B200FA_SPLITS")) want = atoll(e) > 0 ? atoll(e) : want;
+    int64_t len = (n_kv + want - 1) / want;
+    len = (len + 63) / 64 * 64;
+    if (len < 64) len = 64;
+    pl.split_len = (int)len;
+    pl.n_splits = (int)((n_kv + len - 1) / len);
+    if (pl.n_splits < 1) pl.n_splits = 1;
+    if (pl.n_splits > 1 || force_partial_out)
+        pl.part_bytes = align_up((size_t)pl.n_splits * (size_t)(n_batch * n_q * n_head) * (size_t)(D + 2) * 4, 256);
+    pl.total = pl.part_bytes;
+    return pl;
+}
+
+int validate(const void* q, const void* k, const void* v, const void* out, int q_type, int kv_type, int dst_type,
+             int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03, int64_t ne10, int64_t ne11, int64_t ne12,
+             int64_t ne13, const void* mask, int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+             int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23) {
+    if (!q || !k || !v || !out) return B200FA_ERR_INVALID;
+    if (ne00 <= 0 || ne01 <= 0 || ne02 <= 0 || ne03 <= 0 || ne11 <= 0 || ne12 <= 0 || ne13 <= 0) return B200FA_ERR_INVALID;
+    if (ne00 != ne10) return B200FA_ERR_INVALID;
+    if (ne02 % ne12 || ne03 % ne13) return B200FA_ERR_INVALID;
+    if (q_type != B200FA_TYPE_F32 && q_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
+    if (kv_type != B200FA_TYPE_F16 && kv_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
+    if (dst_type != B200FA_TYPE_F32 && dst_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
+    if (ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
+    if (ne11 > 0x7fffffff || ne01 > 0x7fffffff || ne02 > 65535 || ne03 * ne12 > 65535) return B200FA_ERR_UNSUPPORTED;
+    const int64_t qrow = ne00 * (q_type == B200FA_TYPE_F32 ? 4 : 2);
+    if (nb01 < qrow || ((uintptr_t)q | nb01 | nb02 | nb03) % 16) return B200FA_ERR_INVALID;
+    if (kv_type == B200FA_TYPE_F16) {
+        if (nb11 < ne00 * 2 || nb21 < ne00 * 2) return B200FA_ERR_INVALID;
+        if (((uintptr_t)k | (uintptr_t)v | nb11 | nb12 | nb13 | nb21 | nb22 | nb23) % 16) return B200FA_ERR_INVALID;
+    } else {
+        const int64_t row = ne00 / kQ8BlockElems * kQ8BlockBytes;
+        if (nb11 < row || nb21 < row) return B200FA_ERR_INVALID;
+        if (((uintptr_t)k | (uintptr_t)v | nb11 | nb12 | nb13 | nb21 | nb22 | nb23) % 2) return B200FA_ERR_INVALID;
+    }
+    if (mask) {
+        if (ne31 < ne01 || nb31 < ne11 * 2 || ((uintptr_t)mask | nb31) % 2) return B200FA_ERR_INVALID;
+    }
+    if ((uintptr_t)out % 16) return B200FA_ERR_INVALID;
+    return B200FA_OK;
+}
+
+template <int D>
+int launch_rows16(const FaParams& p, int n_groups, cudaStream_t st) {
+    dim3 grid(p.n_splits, n_groups, p.n_head_kv * p.n_batch), block(kDecodeWarps * 32);
+    if (p.kv_type == B200FA_TYPE_F16) fa_rows16_splitkv<D, B200FA_TYPE_F16><<<grid, block, 0, st>>>(p);
+    else fa_rows16_splitkv<D, B200FA_TYPE_Q8_0><<<grid, block, 0, st>>>(p);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+int run_rows16(FaParams& p, const Plan& pl, cudaStream_t st) {
+    int rc = (p.D == 128) ? launch_rows16<128>(p, pl.n_groups, st) : launch_rows16<64>(p, pl.n_groups, st);
+    g_last_launches++;
+    return rc;
+}
+
+template <int D>
+int launch_combine(const float* part, int n_parts, int64_t rows, void* dst, int dst_type, cudaStream_t st) {
+    fa_combine<D><<<(unsigned)rows, D, 0, st>>>(part, n_parts, rows, dst, dst_type);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200fa_status_string(int s) {
+    switch (s) {
+        case B200FA_OK: return "ok";
+        case B200FA_ERR_INVALID: return "invalid argument";
+        case B200FA_ERR_UNSUPPORTED: return "unsupported shape or type";
+        case B200FA_ERR_WORKSPACE: return "workspace missing or too small";
+        case B200FA_ERR_CUDA: return "no sm_100 device or launch failed";
+        default: return "unknown status";
+    }
+}
+
+int b200fa_version(void) { return 100; }
+const char* b200fa_last_dispatch(void) { return g_last_dispatch; }
+int b200fa_last_launch_count(void) { return g_last_launches; }
+
+size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                             int64_t ne11, int64_t ne12, int64_t ne13, uint32_t flags) {
+    const DeviceInfo& di = device_info();
+    const int sms = di.ok ? di.sm_count : 148;
+    if (ne12 <= 0 || ne02 % ne12) return 0;
+    Plan a = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, sms, false);
+    Plan b = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, sms, true);  // _partial entry
+    (void)ne13;
+    return (a.total > b.total ? a.total : b.total) + 256;
+}
+
+static int attn_common(const void* q, const void* k, const void* v, const void* mask, void* dst, float* partial_out,
+                       float scale, int q_type, int kv_type, int dst_type,
+                       int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                       int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                       int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                       int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                       int64_t kv_pos0, int64_t n_kv_total, uint32_t flags, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+    g_last_dispatch = "none";
+    g_last_launches = 0;
+    const bool want_partial = partial_out != nullptr;
+    int rc = validate(q, k, v, want_partial ? (void*)partial_out : dst, q_type, kv_type, dst_type, ne00, ne01, ne02,
+                      ne03, ne10, ne11, ne12, ne13, mask, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23);
+    if (rc != B200FA_OK) return rc;
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;  // sm_100a only, no fallback
+
+    Plan pl = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, di.sm_count, want_partial);
+    if (pl.total > 0 && (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256))) return B200FA_ERR_WORKSPACE;
+
+    FaParams p{};
+    p.q = (const char*)q; p.k = (const char*)k; p.v = (const char*)v; p.mask = (const char*)mask;
+    p.dst = dst; p.part = nullptr;
+    p.scale = scale; p.scale_log2 = scale * kLog2e;
+    p.q_type = q_type; p.kv_type = kv_type; p.dst_type = dst_type;
+    p.D = (int)ne00; p.n_q = (int)ne01; p.n_head = (int)ne02; p.n_batch = (int)ne03;
+    p.n_kv = (int)ne11; p.n_head_kv = (int)ne12; p.n_batch_kv = (int)ne13;
+    p.gqa = (int)(ne02 / ne12); p.rk3 = (int)(ne03 / ne13);
+    p.nb01 = nb01; p.nb02 = nb02; p.nb03 = nb03;
+    p.nb11 = nb11; p.nb12 = nb12; p.nb13 = nb13;
+    p.nb21 = nb21; p.nb22 = nb22; p.nb23 = nb23;
+    p.nb31 = nb31;
+    p.causal = (flags & B200FA_FLAG_CAUSAL) ? 1 : 0;
+    p.kv_pos0 = kv_pos0;
+    p.causal_off = n_kv_total - ne01;
+    p.total_rows = ne03 * ne01 * ne02;
+
+    if (pl.use_prefill) {
+        g_last_dispatch = "prefill_tcgen05";
+        int launches = 0;
+        rc = launch_prefill_tcgen05(p, (char*)workspace, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
+        g_last_launches = launches;
+        return rc;
+    }
+
+    p.n_splits = pl.n_splits; p.split_len = pl.split_len;
+    const int64_t rows = p.total_rows;
+    if (!want_partial) {
+        g_last_dispatch = (ne01 * p.gqa <= 64) ? "decode_splitkv" : "rows16_mma";
+        if (pl.n_splits == 1) {
+            p.write_final = 1;
+            return run_rows16(p, pl, st);
+        }
+        p.write_final = 0; p.part = (float*)workspace;
+        rc = run_rows16(p, pl, st);
+        if (rc != B200FA_OK) return rc;
+        g_last_launches++;
+        return (p.D == 128) ? launch_combine<128>(p.part, pl.n_splits, rows, dst, dst_type, st)
+                            : launch_combine<64>(p.part, pl.n_splits, rows, dst, dst_type, st);
+    }
+    // sequence-split building block: exactly one (O~, m, l) triple per row goes to the caller
+    g_last_dispatch = "decode_splitkv_partial";
+    p.write_final = 0;
+    if (pl.n_splits == 1) {
+        p.part = partial_out;
+        return run_rows16(p, pl, st);
+    }
+    p.part = (float*)workspace;
+    rc = run_rows16(p, pl, st);
+    if (rc != B200FA_OK) return rc;
+    g_last_launches++;
+    if (p.D == 128) fa_combine_to_partial<128><<<(unsigned)rows, 128, 0, st>>>(p.part, pl.n_splits, rows, partial_out);
+    else fa_combine_to_partial<64><<<(unsigned)rows, 64, 0, st>>>(p.part, pl.n_splits, rows, partial_out);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+int b200fa_flash_attn_ext(const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+                          int q_type, int kv_type, int dst_type,
+                          int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                          int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                          int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                          int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                          int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+                          uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    if (ne0 != ne00 || ne1 != ne02 || ne2 != ne01 || ne3 != ne03) return B200FA_ERR_INVALID;  // flash-llama.h:434
+    return attn_common(q, k, v, mask, dst, nullptr, scale, q_type, kv_type, dst_type, ne00, ne01, ne02, ne03, ne10, ne11,
+                       ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, 0, ne11, flags,
+                       workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200fa_flash_attn_partial(const void* q, const void* k, const void* v, const void* mask, float* partial, float scale,
+                              int q_type, int kv_type,
+                              int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                              int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                              int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                              int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                              int64_t kv_pos0, int64_t n_kv_total,
+                              uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    if (!partial || kv_pos0 < 0 || n_kv_total < kv_pos0 + ne11) return B200FA_ERR_INVALID;
+    return attn_common(q, k, v, mask, nullptr, partial, scale, q_type, kv_type, B200FA_TYPE_F32, ne00, ne01, ne02, ne03,
+                       ne10, ne11, ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0,
+                       n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, int64_t D, void* dst, int dst_type,
+                          b200fa_stream_t stream) {
+    if (!partials || !dst || n_parts < 1 || n_rows < 1) return B200FA_ERR_INVALID;
+    if (dst_type != B200FA_TYPE_F32 && dst_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
+    if (D == 128) return launch_combine<128>(partials, n_parts, n_rows, dst, dst_type, (cudaStream_t)stream);
+    if (D == 64) return launch_combine<64>(partials, n_parts, n_rows, dst, dst_type, (cudaStream_t)stream);
+    return B200FA_ERR_UNSUPPORTED;
+}
+
+int b200fa_quantize_q8_0(const void* src, int src_type, void* dst, int64_t n, b200fa_stream_t stream) {
+    if (!src || !dst || n <= 0 || n % kQ8BlockElems) return B200FA_ERR_INVALID;
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
+    const int64_t nb = n / kQ8BlockElems;
+    const unsigned grid = (unsigned)((nb + 7) / 8);
+    if (src_type == B200FA_TYPE_F32) q8_0_quantize_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (uint8_t*)dst, nb);
+    else if (src_type == B200FA_TYPE_F16) q8_0_quantize_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, (uint8_t*)dst, nb);
+    else return B200FA_ERR_UNSUPPORTED;
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n, b200fa_stream_t stream) {
+    if (!src || !dst || n <= 0 || n % kQ8BlockElems) return B200FA_ERR_INVALID;
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
+    const int64_t nb = n / kQ8BlockElems;
+    q8_0_dequantize_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, dst, nb);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+}  // extern "C"

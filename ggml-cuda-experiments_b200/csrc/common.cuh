@@ -1,0 +1,84 @@
+// common.cuh — shared definitions for the b200fa kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200fa.h"
+
+namespace b200fa {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kQ8BlockBytes = 34;
+constexpr int kQ8BlockElems = 32;
+
+// Everything a kernel needs to know about one attention call.  Mirrors the reference kernel's
+// argument list (flash-llama.h:6-32) plus the split-KV bookkeeping of flash_attn_row/fa_reduce.
+struct FaParams {
+    const char* q;
+    const char* k;
+    const char* v;
+    const char* mask;  // f16, may be null
+    void* dst;         // final output (f32/f16), or null when only partials are wanted
+    float* part;       // split-KV partial triples: [split][row][D+2]  (O~[D], m, l)
+    float scale;       // as passed by the caller
+    float scale_log2;  // scale * log2(e)
+    int q_type, kv_type, dst_type;
+    int D, n_q, n_head, n_batch;
+    int n_kv, n_head_kv, n_batch_kv;
+    int gqa;           // rk2 = n_head / n_head_kv   (flash-llama.h:128)
+    int rk3;           // n_batch / n_batch_kv       (flash-llama.h:129)
+    int64_t nb01, nb02, nb03;
+    int64_t nb11, nb12, nb13;
+    int64_t nb21, nb22, nb23;
+    int64_t nb31;
+    int causal;          // B200FA_FLAG_CAUSAL
+    int64_t kv_pos0;     // global position of this slice's first key (sequence-split); 0 otherwise
+    int64_t causal_off;  // a query at iq1 sees global kv positions <= iq1 + causal_off  (n_kv_total - n_q)
+    int n_splits;        // KV splits across CTAs
+    int split_len;       // keys per split (multiple of 16)
+    int64_t total_rows;  // n_batch * n_q * n_head
+    int write_final;     // 1: n_splits == 1 and dst wanted -> normalise in-kernel
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float ld_mask(const char* mask_row, int64_t col) {
+    return __half2float(*reinterpret_cast<const __half*>(mask_row + col * 2));
+}
+
+}  // namespace b200fa

@@ -1,0 +1,142 @@
+/*
+ * b200fa.h — C ABI of the B200-native flash-attention path (sm_100a).
+ *
+ * Drop-in boundary for the launcher interface prototyped in FSSRepo/ggml-cuda-experiments.
+ * The reference has no plugin/FFI layer: its boundary is the kernel signature plus the launch
+ * geometry at the call sites.  Each entry point below names the reference interface it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes; every pointer is caller-owned DEVICE memory unless stated;
+ *   - work is enqueued on `stream` of the CURRENT device; nothing synchronises, nothing allocates;
+ *   - returns B200FA_OK (0) or a negative B200FA_ERR_* code; never aborts.  Asynchronous faults
+ *     surface at the caller's next cudaGetLastError/cudaStreamSynchronize, as with the reference's
+ *     raw <<<>>> launches (flash-matrix.cu:198-206, which check nothing);
+ *   - thread-safe for concurrent calls on distinct streams with distinct workspaces.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every launch entry returns
+ *     B200FA_ERR_CUDA.
+ *
+ * Tensor description is ggml's: ne = element counts, nb = byte strides, fastest dimension first.
+ *   q    : [ne00=D, ne01=n_q,  ne02=n_head,    ne03=n_batch]  f32 (reference) or f16
+ *   k, v : [ne10=D, ne11=n_kv, ne12=n_head_kv, ne13=n_batch_kv] f16, or q8_0 (34-byte blocks of 32)
+ *   mask : f16 [n_kv, ne31 >= n_q] rows = queries, row stride nb31 bytes, shared by heads/batches; may be NULL
+ *   dst  : [D, n_head, n_q, n_batch] contiguous, f32 (reference) or f16
+ *   GQA  : kv head = q head / (ne02/ne12); batch broadcast likewise (flash-llama.h:128-140).
+ */
+#ifndef B200FA_H
+#define B200FA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ggml type tags (values are ggml's GGML_TYPE_*) */
+#define B200FA_TYPE_F32 0
+#define B200FA_TYPE_F16 1
+#define B200FA_TYPE_Q8_0 8
+
+/* flags */
+#define B200FA_FLAG_CAUSAL 1u      /* mask (if given) is exactly the causal one: 0 where kv <= q + (n_kv - n_q),
+                                      -inf elsewhere.  Lets the kernels synthesise it and skip masked tiles. */
+#define B200FA_FLAG_NO_TCGEN05 2u  /* diagnostics: force the register-streaming kernel even for prefill shapes */
+
+/* status codes */
+#define B200FA_OK 0
+#define B200FA_ERR_INVALID (-1)      /* NULL pointer, inconsistent ne/nb, misaligned rows */
+#define B200FA_ERR_UNSUPPORTED (-2)  /* valid but not built: head size, type combination */
+#define B200FA_ERR_WORKSPACE (-3)    /* workspace NULL or smaller than b200fa_workspace_size() */
+#define B200FA_ERR_CUDA (-4)         /* no sm_100 device, or the launch itself failed */
+
+typedef void* b200fa_stream_t; /* a cudaStream_t */
+
+const char* b200fa_status_string(int status);
+int b200fa_version(void); /* major*10000 + minor*100 + patch */
+
+/*
+ * dst = softmax(scale * Q K^T + mask) V
+ *
+ * Replaces:  flash_attn_ext_f16<D,Q,C><<<grid,block,smem,stream>>>(q,k,v,mask,dst,scale, ne.., nb..)
+ *            flash-llama.h:5-32 (signature), launched at flash-matrix.cu:198-206 and kernel_test.h:191-198;
+ *            and, for batch-1 decode, the pair
+ *            flash_attn_row<128,8,2,256> + fa_reduce<128,8>   flash_row_float.h:4-6, :415-416,
+ *            launched at flash-matrix.cu:226-227 and kernel_test.h:161-162
+ *            (whose V^T / dense-K repacking and cudaMalloc'd scratch the caller no longer needs).
+ * The argument list is the reference's, widened to int64 and extended by: type tags (the reference
+ * fixes f32 Q / f16 KV / f32 dst), separate V strides (the reference aliases nb2x = nb1x,
+ * flash-llama.h:123-125), flags, a caller-owned workspace (the reference cudaMallocs its split-KV
+ * scratch at flash-matrix.cu:223-224) and the stream.
+ *
+ * Dispatch (all on the GPU):
+ *   n_q * (n_head/n_head_kv) <= 64  -> split-KV register-streaming kernel + combine (decode; HBM-bound)
+ *   otherwise, D == 128, f16 K/V    -> tcgen05/TMEM/TMA tile kernel (prefill; tensor-bound)
+ *   otherwise                       -> the register-streaming kernel over 16-row groups
+ * Requirements: D in {64, 128}; rows of q/k/v 16-byte aligned for f16/f32 (nb % 16 == 0), 2-byte for q8_0.
+ */
+int b200fa_flash_attn_ext(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+    uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
+
+/* Bytes of workspace b200fa_flash_attn_ext needs for this shape on the current device
+ * (split-KV partials, an f16 copy of an f32 Q for the tcgen05 path, mask tile classes).
+ * Replaces the inline cudaMalloc of flash-matrix.cu:223-224 / kernel_test.h:153-155. */
+size_t b200fa_workspace_size(
+    int q_type, int kv_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne11, int64_t ne12, int64_t ne13, uint32_t flags);
+
+/*
+ * Sequence-split building blocks (cross-GPU split-KV).  Same maths as the reference's intra-GPU pair
+ * flash_attn_row (per-block partial O, m, l; flash_row_float.h:164-197) and fa_reduce (:415-472),
+ * with the state kept in f32 instead of f16.
+ *
+ * b200fa_flash_attn_partial: like b200fa_flash_attn_ext over THIS device's slice of the KV sequence, but
+ * instead of dst it writes, per output row r = (batch*n_q + q)*n_head + head, the unnormalised triple
+ *     partial[r*(D+2) + 0..D-1] = sum_kv exp(s - m) * V      partial[r*(D+2) + D] = m      [.. + D+1] = l
+ * with s = scale*q.k + mask in natural-log units; m = -inf and l = 0 for a row that saw no visible key.
+ * `kv_pos0` is the global position of this slice's first key (used only with B200FA_FLAG_CAUSAL).
+ */
+int b200fa_flash_attn_partial(
+    const void* q, const void* k, const void* v, const void* mask, float* partial, float scale,
+    int q_type, int kv_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t kv_pos0, int64_t n_kv_total,
+    uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
+
+/* Merge n_parts partial triples per row (partials[p][n_rows][D+2], e.g. the all-gathered per-GPU
+ * results) into dst[n_rows][D].  Replaces fa_reduce<128,nw> (flash_row_float.h:415-472). */
+int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, int64_t D,
+                          void* dst, int dst_type, b200fa_stream_t stream);
+
+/*
+ * ggml q8_0 rows (block {f16 d; int8 qs[32]}, 34 bytes).  Not in the reference;
+ * format and rounding are ggml's published ones.  n_elements % 32 == 0.
+ *   quantize : d = amax/127 (stored f16), q = roundf(x * (1/d))       src f32 or f16
+ *   dequantize: y = f32(d) * q                                         bit-exact, dst f32
+ */
+int b200fa_quantize_q8_0(const void* src, int src_type, void* dst, int64_t n_elements, b200fa_stream_t stream);
+int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n_elements, b200fa_stream_t stream);
+
+/* Diagnostics: name of the kernel family the last b200fa_flash_attn_ext call on this thread dispatched to
+ * ("decode_splitkv", "prefill_tcgen05", "rows16_mma"), and how many kernels it launched. */
+const char* b200fa_last_dispatch(void);
+int b200fa_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FA_H */

@@ -1,0 +1,234 @@
+"""-m gpu parity tests for the split-KV decode / rows16 path, through the C ABI, against the CPU oracle,
+the committed reference-host goldens, and the reference's own CUDA kernels (oracle/_ref/libref_gpu.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from common import assert_close, load_ref_host_cases, make_mask, synth_qkv
+from gpu_common import kv_cache_view, pkg, run_both, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- BASELINE.json configs[0]: the repo's flash-matrix test ----
+@pytest.mark.parametrize("mask_kind", ["zeros", "tail56", "none"])
+def test_c1_flash_matrix_case(mask_kind):
+    Q, K, V = synth_qkv(128, 1, 256, 1, 1)
+    run_both(Q, K, V, make_mask(mask_kind, 1, 256), mask_pad=32)
+    assert pkg().last_dispatch() == "decode_splitkv"
+
+
+@pytest.mark.parametrize("tag", ["c1_zero", "c1_tail", "c1_nomask", "llama_32h", "gqa_causal", "noise_mask", "d64"])
+def test_against_reference_host_goldens(tag):
+    """Product vs the outputs of the reference's own host attention (tests/golden/ref_host_cases.npz)."""
+    import torch
+    g = load_ref_host_cases()
+    D, n_q, n_kv, n_head, n_head_kv, s1, s2, s3 = [int(x) for x in g[tag + "__meta"]]
+    Q, K, V = synth_qkv(D, n_q, n_kv, n_head, n_head_kv, 1, (s1, s2, s3))
+    mask = make_mask(str(g[tag + "__mask"]), n_q, n_kv)
+    P = pkg()
+    out = P.flash_attn_ext(to_dev(Q), to_dev(K), to_dev(V), to_dev(mask) if mask is not None else None)
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy()[0], g[tag], tag)
+
+
+# ---- BASELINE.json configs[1]: LLaMA-7B decode, KV-cache view strides + padded mask ----
+def test_c2_llama7b_decode_kv4096_cache_view():
+    Q, K, V = synth_qkv(128, 1, 4096, 32, 32)
+    run_both(Q, K, V, make_mask("zeros", 1, 4096), cache_view=True, mask_pad=32)
+    assert pkg().last_dispatch() == "decode_splitkv"
+    assert pkg().last_launch_count() == 2  # split kernel + combine
+
+
+@pytest.mark.parametrize("n_kv", [1, 15, 16, 17, 77, 255, 256, 257, 1000, 5000])
+def test_ragged_kv_lengths_gqa(n_kv):
+    Q, K, V = synth_qkv(128, 1, n_kv, 32, 8)
+    run_both(Q, K, V, make_mask("noise", 1, n_kv))
+
+
+@pytest.mark.parametrize("n_q,H,Hk", [(1, 8, 1), (2, 32, 8), (5, 32, 8), (3, 16, 16), (16, 4, 4), (40, 8, 2)])
+def test_several_queries_causal_mask_tensor_and_flag(n_q, H, Hk):
+    n_kv = 300
+    Q, K, V = synth_qkv(128, n_q, n_kv, H, Hk)
+    mask = make_mask("causal", n_q, n_kv)
+    a, _ = run_both(Q, K, V, mask, flags=pkg().FLAG_NO_TCGEN05)
+    b, _ = run_both(Q, K, V, mask, flags=pkg().FLAG_CAUSAL | pkg().FLAG_NO_TCGEN05)
+    c, _ = run_both(Q, K, V, None, flags=pkg().FLAG_CAUSAL | pkg().FLAG_NO_TCGEN05)  # synthesised mask
+    assert np.abs(a - b).max() < 1e-5 and np.abs(b - c).max() < 1e-5
+
+
+def test_f16_q_and_f16_dst():
+    Q, K, V = synth_qkv(128, 1, 700, 32, 8)
+    run_both(Q, K, V, None, q_f16=True, dst_f16=True)
+
+
+def test_head_dim_64():
+    Q, K, V = synth_qkv(64, 2, 333, 8, 4)
+    run_both(Q, K, V, make_mask("causal", 2, 333))
+
+
+def test_batch_and_batch_broadcast():
+    Q, K, V = synth_qkv(128, 1, 513, 8, 2, n_batch=3)
+    run_both(Q, K, V, make_mask("noise", 1, 513), cache_view=True)
+    # batch broadcast (ne03 = 4, ne13 = 2 -> ik3 = iq3 / 2, flash-llama.h:129,137)
+    Q4 = oracle.uniform_pm1(1, (4, 8, 1, 128)); _, K2, V2 = synth_qkv(128, 1, 200, 8, 2, n_batch=2)
+    run_both(Q4, K2, V2, None)
+
+
+def test_fully_masked_rows_give_zeros_not_nan():
+    import torch
+    Q, K, V = synth_qkv(128, 2, 64, 4, 4)
+    mask = np.zeros((2, 64), np.float16); mask[1, :] = -np.inf; mask[0, :10] = -np.inf
+    got, ref = run_both(Q, K, V, mask)
+    assert np.all(got[0, 1] == 0)
+
+
+# ---- q8_0 K/V (BASELINE.json configs[4], reduced) ----
+@pytest.mark.parametrize("n_kv,H,Hk", [(256, 32, 8), (1000, 32, 8), (4096, 8, 8)])
+def test_q8_0_kv_in_loop_dequant(n_kv, H, Hk):
+    Q, K, V = synth_qkv(128, 1, n_kv, H, Hk)
+    run_both(Q, K, V, None, q8=True)
+
+
+def test_q8_0_quantize_dequantize_kernels_bit_exact():
+    import torch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "q8_0_gguf.npz"))
+    P = pkg()
+    qb = P.quantize_q8_0(to_dev(g["x"]))
+    np.testing.assert_array_equal(qb.cpu().numpy(), g["blocks"])
+    dq = P.dequantize_q8_0(to_dev(g["blocks"]))
+    np.testing.assert_array_equal(dq.cpu().numpy().view(np.uint32), g["dequant"].view(np.uint32))
+    x = oracle.uniform_pm1(9, (64, 4096)).astype(np.float32) * 3
+    np.testing.assert_array_equal(P.quantize_q8_0(to_dev(x)).cpu().numpy(), oracle.quantize_q8_0(x))
+    np.testing.assert_array_equal(P.quantize_q8_0(to_dev(x.astype(np.float16))).cpu().numpy(),
+                                  oracle.quantize_q8_0(x.astype(np.float16).astype(np.float32)))
+
+
+# ---- sequence-split building blocks (C5 path): partial triples + merge == unsplit ----
+@pytest.mark.parametrize("q8", [False, True])
+@pytest.mark.parametrize("n_parts", [2, 8])
+def test_partials_merge_equals_unsplit(n_parts, q8):
+    import torch
+    P = pkg()
+    n_kv, H, Hk = 2048, 32, 8
+    Q, K, V = synth_qkv(128, 1, n_kv, H, Hk)
+    if q8:
+        Kq, Vq = oracle.quantize_q8_0(K.astype(np.float32)), oracle.quantize_q8_0(V.astype(np.float32))
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(Kq, 8), oracle.view_of(Vq, 8), None, 1 / np.sqrt(128),
+                                    round_q_f16=True)
+        k, v = to_dev(Kq), to_dev(Vq)
+    else:
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), None, 1 / np.sqrt(128),
+                                    round_q_f16=True)
+        k, v = to_dev(K), to_dev(V)
+    q = to_dev(Q)
+    step = n_kv // n_parts
+    parts = [P.flash_attn_partial(q, k[:, :, i * step:(i + 1) * step], v[:, :, i * step:(i + 1) * step],
+                                  kv_pos0=i * step, n_kv_total=n_kv) for i in range(n_parts)]
+    out = P.merge_partials(torch.stack(parts))
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy().reshape(ref.shape), ref, "partials+merge")
+    # the triples themselves: m = row max in natural units, l = sum exp(s - m)
+    p0 = parts[0].cpu().numpy()
+    Kf = oracle.dequantize_q8_0(Kq) if q8 else K.astype(np.float32)
+    s = (Q[0, 0, 0].astype(np.float16).astype(np.float64) @ Kf[0, 0, :step].astype(np.float64).T) / np.sqrt(128)
+    assert abs(p0[0, 128] - s.max()) < 2e-3
+    assert abs(p0[0, 129] - np.exp(s - s.max()).sum()) / np.exp(s - s.max()).sum() < 2e-3
+
+
+def test_partial_with_causal_flag_and_positions():
+    import torch
+    P = pkg()
+    n_q, n_kv, H, Hk = 4, 512, 8, 2
+    Q, K, V = synth_qkv(128, n_q, n_kv, H, Hk)
+    mask = make_mask("causal", n_q, n_kv)
+    ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), oracle.view_of(mask),
+                                1 / np.sqrt(128), round_q_f16=True)
+    q, k, v = to_dev(Q), to_dev(K), to_dev(V)
+    parts = [P.flash_attn_partial(q, k[:, :, i * 128:(i + 1) * 128], v[:, :, i * 128:(i + 1) * 128], kv_pos0=i * 128,
+                                  n_kv_total=n_kv, flags=P.FLAG_CAUSAL) for i in range(4)]
+    out = P.merge_partials(torch.stack(parts))
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy().reshape(ref.shape), ref, "causal partials")
+
+
+# ---- the reference's own CUDA kernels on the same B200 (legacy HMMA path) ----
+def _ref_gpu():
+    path = oracle.ref_gpu_path()
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_gpu.so not built")
+    return C.CDLL(path)
+
+
+@pytest.mark.parametrize("n_kv", [256, 512, 4096])
+def test_vs_reference_cuda_flash_attn_row(n_kv):
+    """flash_attn_row<128,8,2,256> + fa_reduce<128,8> (flash_row_float.h) vs ours, same inputs (kernel_test.h recipe)."""
+    import torch
+    lib = _ref_gpu()
+    P = pkg()
+    H, Hk, D = 32, 8, 128
+    Q, K, V = synth_qkv(D, 1, n_kv, H, Hk)
+    mask1d = make_mask("noise", 1, n_kv)
+    ours, ref32 = run_both(Q, K, V, mask1d)
+    q = to_dev(Q[0, :, 0, :]); k = to_dev(K[0]); vT = to_dev(np.ascontiguousarray(V[0].transpose(0, 2, 1)))
+    m = to_dev(mask1d[0])
+    lib.ref_gpu_row_tmp_halves.restype = C.c_size_t
+    tmp = torch.zeros(lib.ref_gpu_row_tmp_halves(n_kv, H), dtype=torch.float16, device="cuda")
+    dst = torch.zeros(H, D, dtype=torch.float32, device="cuda")
+    rc = lib.ref_gpu_flash_attn_row(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(vT.data_ptr()),
+                                    C.c_void_p(m.data_ptr()), C.c_void_p(tmp.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                    n_kv, C.c_float(1 / np.sqrt(D)), H, H // Hk, None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    refgpu = dst.cpu().numpy()
+    e_ref = np.abs(refgpu - ref32[0, 0]).max()
+    e_new = np.abs(ours[0, 0] - ref32[0, 0]).max()
+    e_x = np.abs(ours[0, 0] - refgpu).max()
+    print(f"n_kv={n_kv}: ours-fp32 {e_new:.2e}  refgpu-fp32 {e_ref:.2e}  ours-refgpu {e_x:.2e}")
+    # gate ours-vs-refgpu only where the f16-accumulating reference is itself inside tolerance
+    if np.all(np.abs(refgpu - ref32[0, 0]) <= 2e-3 + 1e-2 * np.abs(ref32[0, 0])):
+        assert_close(ours[0, 0], refgpu, "ours vs reference CUDA", atol=4e-3, rtol=2e-2)
+
+
+def test_vs_reference_cuda_flash_attn_ext_f16_decode():
+    """flash_attn_ext_f16<128,16,128> (flash-llama.h) on the kernel_test shape (kernel_test.h:191-198)."""
+    import torch
+    lib = _ref_gpu()
+    H, Hk, D, n_kv = 32, 8, 128, 512
+    Q, K, V = synth_qkv(D, 1, n_kv, H, Hk)
+    mask = make_mask("noise", 1, n_kv)
+    ours, ref32 = run_both(Q, K, V, mask, mask_pad=32)
+    q = to_dev(Q[0, :, 0, :]); k = to_dev(K[0]); v = to_dev(V[0])
+    mp = np.zeros((32, n_kv), np.float16); mp[0] = mask[0]
+    m = to_dev(mp)
+    dst = torch.zeros(H, D, dtype=torch.float32, device="cuda")
+    rc = lib.ref_gpu_flash_attn_ext_f16(
+        C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), C.c_void_p(m.data_ptr()),
+        C.c_void_p(dst.data_ptr()), C.c_float(1 / np.sqrt(D)), D, 1, H, 1, D, n_kv, Hk, 1, 32, n_kv * 2,
+        D * 4, D * 4, D * H * 4, D * 2, D * n_kv * 2, D * n_kv * Hk * 2, D, H, 1, 1, None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    refgpu = dst.cpu().numpy()
+    print(f"ext_f16: ours-fp32 {np.abs(ours[0,0]-ref32[0,0]).max():.2e} refgpu-fp32 {np.abs(refgpu-ref32[0,0]).max():.2e} "
+          f"ours-refgpu {np.abs(ours[0,0]-refgpu).max():.2e}")
+    if np.all(np.abs(refgpu - ref32[0, 0]) <= 2e-3 + 1e-2 * np.abs(ref32[0, 0])):
+        assert_close(ours[0, 0], refgpu, "ours vs reference CUDA ext_f16", atol=4e-3, rtol=2e-2)
+
+
+def test_error_paths_on_device():
+    import torch
+    P = pkg()
+    q = torch.zeros(1, 4, 1, 128, device="cuda"); k = torch.zeros(1, 2, 64, 128, dtype=torch.float16, device="cuda")
+    with pytest.raises(P.B200FAError) as e:
+        P.flash_attn_ext(q, k, k, workspace=P.Workspace(0), flags=0, mask=None, scale=1.0,
+                         dst=torch.zeros(1, 1, 5, 128, device="cuda"))  # wrong dst head count is caught by ne check
+    Q, K, V = synth_qkv(128, 1, 4096, 32, 32)
+    class Tiny(P.Workspace):
+        def __init__(self):
+            super().__init__(256); self.nbytes = 256
+    with pytest.raises(P.B200FAError) as e:
+        P.flash_attn_ext(to_dev(Q), to_dev(K), to_dev(V), workspace=Tiny())
+    assert e.value.status == -3
