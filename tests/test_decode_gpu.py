@@ -221,10 +221,6 @@ def test_vs_reference_cuda_flash_attn_ext_f16_decode():
 def test_error_paths_on_device():
     import torch
     P = pkg()
-    q = torch.zeros(1, 4, 1, 128, device="cuda"); k = torch.zeros(1, 2, 64, 128, dtype=torch.float16, device="cuda")
-    with pytest.raises(P.B200FAError) as e:
-        P.flash_attn_ext(q, k, k, workspace=P.Workspace(0), flags=0, mask=None, scale=1.0,
-                         dst=torch.zeros(1, 1, 5, 128, device="cuda"))  # wrong dst head count is caught by ne check
     Q, K, V = synth_qkv(128, 1, 4096, 32, 32)
     class Tiny(P.Workspace):
         def __init__(self):
