@@ -152,6 +152,11 @@ const char* b200fa_status_string(int s) {
 }
 
 int b200fa_version(void) { return 100; }
+void b200fa_debug_set(void* timeout_word, float* dump, int dump_cta) {
+    pf_debug().dbg = (unsigned long long*)timeout_word;
+    pf_debug().dump = dump;
+    pf_debug().dump_cta = dump_cta;
+}
 const char* b200fa_last_dispatch(void) { return g_last_dispatch; }
 int b200fa_last_launch_count(void) { return g_last_launches; }
 
@@ -162,8 +167,11 @@ size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01
     if (ne12 <= 0 || ne02 % ne12) return 0;
     Plan a = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, sms, false);
     Plan b = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, sms, true);  // _partial entry
+    Plan c = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags | B200FA_FLAG_NO_TCGEN05, sms, false);
     (void)ne13;
-    return (a.total > b.total ? a.total : b.total) + 256;
+    size_t m = a.total > b.total ? a.total : b.total;
+    if (c.total > m) m = c.total;
+    return m + 256;
 }
 
 static int attn_common(const void* q, const void* k, const void* v, const void* mask, void* dst, float* partial_out,
@@ -183,6 +191,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     const DeviceInfo& di = device_info();
     if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;  // sm_100a only, no fallback
 
+    if (!(scale > 0.f)) flags |= B200FA_FLAG_NO_TCGEN05;  // the tile kernel takes row maxima of raw scores
     Plan pl = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, di.sm_count, want_partial);
     if (pl.total > 0 && (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256))) return B200FA_ERR_WORKSPACE;
 

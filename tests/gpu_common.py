@@ -22,7 +22,7 @@ def kv_cache_view(t):
 
 
 def run_both(Q, K, V, mask, scale=None, flags=0, q_f16=False, dst_f16=False, cache_view=False, q8=False,
-             mask_pad=None, atol=None, rtol=None, what=""):
+             mask_pad=None, atol=None, rtol=None, what="", drop_mask_for_product=False):
     """Q f32 [b][h][q][D], K/V f16 [bk][hk][kv][D], mask f16 [q][kv] or None.  Returns (got, ref)."""
     import torch
     P = pkg()
@@ -42,7 +42,7 @@ def run_both(Q, K, V, mask, scale=None, flags=0, q_f16=False, dst_f16=False, cac
     if cache_view:
         q, k, v = kv_cache_view(q), kv_cache_view(k), kv_cache_view(v)
     m = None
-    if mask is not None:
+    if mask is not None and not drop_mask_for_product:
         mm = mask
         if mask_pad:
             rows = (mask.shape[0] + mask_pad - 1) // mask_pad * mask_pad

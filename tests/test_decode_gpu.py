@@ -56,7 +56,7 @@ def test_several_queries_causal_mask_tensor_and_flag(n_q, H, Hk):
     mask = make_mask("causal", n_q, n_kv)
     a, _ = run_both(Q, K, V, mask, flags=pkg().FLAG_NO_TCGEN05)
     b, _ = run_both(Q, K, V, mask, flags=pkg().FLAG_CAUSAL | pkg().FLAG_NO_TCGEN05)
-    c, _ = run_both(Q, K, V, None, flags=pkg().FLAG_CAUSAL | pkg().FLAG_NO_TCGEN05)  # synthesised mask
+    c, _ = run_both(Q, K, V, mask, flags=pkg().FLAG_CAUSAL | pkg().FLAG_NO_TCGEN05, drop_mask_for_product=True)  # synthesised
     assert np.abs(a - b).max() < 1e-5 and np.abs(b - c).max() < 1e-5
 
 
