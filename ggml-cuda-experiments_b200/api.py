@@ -12,7 +12,7 @@ import os
 from .build import LIB, build
 
 TYPE_F32, TYPE_F16, TYPE_Q8_0 = 0, 1, 8
-FLAG_CAUSAL, FLAG_NO_TCGEN05 = 1, 2
+FLAG_CAUSAL, FLAG_NO_TCGEN05, FLAG_SKIP_COMBINE = 1, 2, 4
 Q8_BLOCK_BYTES, Q8_BLOCK_ELEMS = 34, 32
 
 _lib = None

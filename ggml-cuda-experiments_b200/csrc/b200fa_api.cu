@@ -231,6 +231,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
         p.write_final = 0; p.part = (float*)workspace;
         rc = run_rows16(p, pl, st);
         if (rc != B200FA_OK) return rc;
+        if (flags & B200FA_FLAG_SKIP_COMBINE) return B200FA_OK;
         g_last_launches++;
         return (p.D == 128) ? launch_combine<128>(p.part, pl.n_splits, rows, dst, dst_type, st)
                             : launch_combine<64>(p.part, pl.n_splits, rows, dst, dst_type, st);

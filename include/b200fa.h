@@ -41,6 +41,8 @@ extern "C" {
 #define B200FA_FLAG_CAUSAL 1u      /* mask (if given) is exactly the causal one: 0 where kv <= q + (n_kv - n_q),
                                       -inf elsewhere.  Lets the kernels synthesise it and skip masked tiles. */
 #define B200FA_FLAG_NO_TCGEN05 2u  /* diagnostics: force the register-streaming kernel even for prefill shapes */
+#define B200FA_FLAG_SKIP_COMBINE 4u /* measurement only: launch the split-KV kernel without its combine (dst is NOT
+                                      written) so bench.py can time the dominant kernel by itself */
 
 /* status codes */
 #define B200FA_OK 0
