@@ -12,7 +12,7 @@ import os
 from .build import LIB, build
 
 TYPE_F32, TYPE_F16, TYPE_Q8_0 = 0, 1, 8
-FLAG_CAUSAL, FLAG_NO_TCGEN05, FLAG_SKIP_COMBINE = 1, 2, 4
+FLAG_CAUSAL, FLAG_NO_TCGEN05, FLAG_WORKSPACE_ZEROED = 1, 2, 4
 Q8_BLOCK_BYTES, Q8_BLOCK_ELEMS = 34, 32
 
 _lib = None
@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
         l.b200fa_flash_attn_partial.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 2 + [i64] * 21 + [C.c_uint32, vp, C.c_size_t, vp]
         l.b200fa_workspace_size.restype = C.c_size_t
         l.b200fa_workspace_size.argtypes = [C.c_int, C.c_int] + [i64] * 7 + [C.c_uint32]
+        l.b200fa_workspace_init.restype = C.c_int
+        l.b200fa_workspace_init.argtypes = [vp, C.c_size_t, vp]
         l.b200fa_merge_partials.restype = C.c_int
         l.b200fa_merge_partials.argtypes = [vp, C.c_int, i64, i64, vp, C.c_int, vp]
         l.b200fa_quantize_q8_0.restype = C.c_int
@@ -96,7 +98,7 @@ class Workspace:
     def __init__(self, nbytes: int, device=None):
         import torch
         self.nbytes = max(int(nbytes), 256)
-        self.buf = torch.empty(self.nbytes + 256, dtype=torch.uint8, device=device or "cuda")
+        self.buf = torch.zeros(self.nbytes + 256, dtype=torch.uint8, device=device or "cuda")  # zero-filled once
         self.ptr = (self.buf.data_ptr() + 255) // 256 * 256
 
 

@@ -46,6 +46,7 @@ struct Plan {
     size_t part_bytes = 0;   // split-KV partials
     size_t qf16_bytes = 0;   // f16 copy of an f32 Q (tcgen05 path)
     size_t cls_bytes = 0;    // mask tile classes (tcgen05 path)
+    size_t ctr_bytes = 0;    // split-KV arrival counters (after the partials)
     size_t total = 0;
 };
 
@@ -65,24 +66,40 @@ Plan make_plan(int q_type, int kv_type, int64_t D, int64_t n_q, int64_t n_head, 
     }
     pl.n_groups = (int)((rows + kRows - 1) / kRows);
     const int64_t base = (int64_t)pl.n_groups * n_head_kv * n_batch;
-    int64_t target = (int64_t)sm_count * 12;  // ~3 resident CTAs per SM x 4 waves
-    if (const char* e = getenv("B200FA_TARGET_CTAS")) target = atoll(e);
-    int64_t want = (target + base - 1) / base;
-    const int64_t min_keys = 256;
-    int64_t max_splits = (n_kv + min_keys - 1) / min_keys;
+    // Split planning: fill whole waves of resident CTAs (2 per SM).  Candidates keep >= 256 keys per split; pick
+    // the fewest splits whose wave efficiency is within 3% of the best.
+    const int64_t slots = (int64_t)sm_count * 2;
+    int64_t max_splits = n_kv / 256;
     if (max_splits < 1) max_splits = 1;
-    if (want > max_splits) want = max_splits;
-    if (want < 1) want = 1;
+    if (max_splits > 64) max_splits = 64;
+    int64_t want = 1;
+    if (base * max_splits <= slots) {
+        want = max_splits;  // everything fits in one wave: be as parallel as allowed
+    } else {
+        double best = 0.0;
+        for (int64_t n = 1; n <= max_splits; n++) {
+            const int64_t ctas = base * n, waves = (ctas + slots - 1) / slots;
+            const double eff = (double)ctas / (double)(waves * slots);
+            if (eff > best) best = eff;
+        }
+        for (int64_t n = 1; n <= max_splits; n++) {
+            const int64_t ctas = base * n, waves = (ctas + slots - 1) / slots;
+            const double eff = (double)ctas / (double)(waves * slots);
+            if (eff >= best - 0.03) { want = n; break; }
+        }
+    }
     if (const char* e = getenv("B200FA_SPLITS")) want = atoll(e) > 0 ? atoll(e) : want;
     int64_t len = (n_kv + want - 1) / want;
-    len = (len + 63) / 64 * 64;
-    if (len < 64) len = 64;
+    len = (len + 15) / 16 * 16;
+    if (len < 16) len = 16;
     pl.split_len = (int)len;
     pl.n_splits = (int)((n_kv + len - 1) / len);
     if (pl.n_splits < 1) pl.n_splits = 1;
-    if (pl.n_splits > 1 || force_partial_out)
+    if (pl.n_splits > 1) {
         pl.part_bytes = align_up((size_t)pl.n_splits * (size_t)(n_batch * n_q * n_head) * (size_t)(D + 2) * 4, 256);
-    pl.total = pl.part_bytes;
+        pl.ctr_bytes = align_up((size_t)base * 4, 256);
+    }
+    pl.total = pl.part_bytes + pl.ctr_bytes;
     return pl;
 }
 
@@ -116,16 +133,35 @@ int validate(const void* q, const void* k, const void* v, const void* out, int q
     return B200FA_OK;
 }
 
-template <int D>
+template <int D, int RH>
 int launch_rows16(const FaParams& p, int n_groups, cudaStream_t st) {
     dim3 grid(p.n_splits, n_groups, p.n_head_kv * p.n_batch), block(kDecodeWarps * 32);
-    if (p.kv_type == B200FA_TYPE_F16) fa_rows16_splitkv<D, B200FA_TYPE_F16><<<grid, block, 0, st>>>(p);
-    else fa_rows16_splitkv<D, B200FA_TYPE_Q8_0><<<grid, block, 0, st>>>(p);
+    constexpr int smem = FifoGeom<D>::kCtaBytes;  // cp.async FIFO (f16) / merge buffers (both)
+    static thread_local bool attr_set[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int ti = p.kv_type == B200FA_TYPE_F16 ? 0 : 1;
+    if (dev >= 0 && dev < 64 && !attr_set[dev][ti]) {
+        cudaError_t e = ti == 0 ? cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                : cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return B200FA_ERR_CUDA;
+        attr_set[dev][ti] = true;
+    }
+    static const int pipe = getenv("B200FA_DECODE_PIPE") ? atoi(getenv("B200FA_DECODE_PIPE")) : 1;
+    if (ti == 0 && pipe == 0) {
+        static thread_local bool a2[64] = {};
+        if (!a2[dev]) { cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a2[dev] = true; }
+        fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false><<<grid, block, smem, st>>>(p);
+    } else if (ti == 0) fa_rows16_splitkv<D, B200FA_TYPE_F16, RH><<<grid, block, smem, st>>>(p);
+    else fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH><<<grid, block, smem, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int run_rows16(FaParams& p, const Plan& pl, cudaStream_t st) {
-    int rc = (p.D == 128) ? launch_rows16<128>(p, pl.n_groups, st) : launch_rows16<64>(p, pl.n_groups, st);
+    const bool small = (int64_t)p.n_q * p.gqa <= 8;  // one group of at most 8 rows: only fragment rows g are live
+    int rc;
+    if (p.D == 128) rc = small ? launch_rows16<128, 1>(p, pl.n_groups, st) : launch_rows16<128, 2>(p, pl.n_groups, st);
+    else rc = small ? launch_rows16<64, 1>(p, pl.n_groups, st) : launch_rows16<64, 2>(p, pl.n_groups, st);
     g_last_launches++;
     return rc;
 }
@@ -211,6 +247,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.kv_pos0 = kv_pos0;
     p.causal_off = n_kv_total - ne01;
     p.total_rows = ne03 * ne01 * ne02;
+    { static const int dm = getenv("B200FA_DBG_MODE") ? atoi(getenv("B200FA_DBG_MODE")) : 0; p.dbg_mode = dm; }
 
     if (pl.use_prefill) {
         g_last_dispatch = "prefill_tcgen05";
@@ -221,35 +258,16 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     }
 
     p.n_splits = pl.n_splits; p.split_len = pl.split_len;
-    const int64_t rows = p.total_rows;
-    if (!want_partial) {
-        g_last_dispatch = (ne01 * p.gqa <= 64) ? "decode_splitkv" : "rows16_mma";
-        if (pl.n_splits == 1) {
-            p.write_final = 1;
-            return run_rows16(p, pl, st);
+    p.part_out = partial_out;
+    g_last_dispatch = want_partial ? "decode_splitkv_partial" : ((ne01 * p.gqa <= 64) ? "decode_splitkv" : "rows16_mma");
+    if (pl.n_splits > 1) {
+        p.part = (float*)workspace;
+        p.counters = (unsigned int*)((char*)workspace + pl.part_bytes);
+        if (!(flags & B200FA_FLAG_WORKSPACE_ZEROED)) {
+            if (cudaMemsetAsync(p.counters, 0, pl.ctr_bytes, st) != cudaSuccess) return B200FA_ERR_CUDA;
         }
-        p.write_final = 0; p.part = (float*)workspace;
-        rc = run_rows16(p, pl, st);
-        if (rc != B200FA_OK) return rc;
-        if (flags & B200FA_FLAG_SKIP_COMBINE) return B200FA_OK;
-        g_last_launches++;
-        return (p.D == 128) ? launch_combine<128>(p.part, pl.n_splits, rows, dst, dst_type, st)
-                            : launch_combine<64>(p.part, pl.n_splits, rows, dst, dst_type, st);
     }
-    // sequence-split building block: exactly one (O~, m, l) triple per row goes to the caller
-    g_last_dispatch = "decode_splitkv_partial";
-    p.write_final = 0;
-    if (pl.n_splits == 1) {
-        p.part = partial_out;
-        return run_rows16(p, pl, st);
-    }
-    p.part = (float*)workspace;
-    rc = run_rows16(p, pl, st);
-    if (rc != B200FA_OK) return rc;
-    g_last_launches++;
-    if (p.D == 128) fa_combine_to_partial<128><<<(unsigned)rows, 128, 0, st>>>(p.part, pl.n_splits, rows, partial_out);
-    else fa_combine_to_partial<64><<<(unsigned)rows, 64, 0, st>>>(p.part, pl.n_splits, rows, partial_out);
-    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    return run_rows16(p, pl, st);
 }
 
 int b200fa_flash_attn_ext(const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
@@ -278,6 +296,11 @@ int b200fa_flash_attn_partial(const void* q, const void* k, const void* v, const
     return attn_common(q, k, v, mask, nullptr, partial, scale, q_type, kv_type, B200FA_TYPE_F32, ne00, ne01, ne02, ne03,
                        ne10, ne11, ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0,
                        n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200fa_workspace_init(void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    if (!workspace || !workspace_bytes) return B200FA_ERR_INVALID;
+    return cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, int64_t D, void* dst, int dst_type,

@@ -22,6 +22,8 @@ struct FaParams {
     const char* mask;  // f16, may be null
     void* dst;         // final output (f32/f16), or null when only partials are wanted
     float* part;       // split-KV partial triples: [split][row][D+2]  (O~[D], m, l)
+    float* part_out;   // sequence-split entry: one merged triple per row goes here instead of dst
+    unsigned int* counters;  // one arrival counter per (row group, kv head, batch); zero between calls
     float scale;       // as passed by the caller
     float scale_log2;  // scale * log2(e)
     int q_type, kv_type, dst_type;
@@ -39,7 +41,7 @@ struct FaParams {
     int n_splits;        // KV splits across CTAs
     int split_len;       // keys per split (multiple of 16)
     int64_t total_rows;  // n_batch * n_q * n_head
-    int write_final;     // 1: n_splits == 1 and dst wanted -> normalise in-kernel
+    int dbg_mode;        // tuning only (env B200FA_DBG_MODE): 1 = stream K/V but skip the tile maths
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {

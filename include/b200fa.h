@@ -41,8 +41,9 @@ extern "C" {
 #define B200FA_FLAG_CAUSAL 1u      /* mask (if given) is exactly the causal one: 0 where kv <= q + (n_kv - n_q),
                                       -inf elsewhere.  Lets the kernels synthesise it and skip masked tiles. */
 #define B200FA_FLAG_NO_TCGEN05 2u  /* diagnostics: force the register-streaming kernel even for prefill shapes */
-#define B200FA_FLAG_SKIP_COMBINE 4u /* measurement only: launch the split-KV kernel without its combine (dst is NOT
-                                      written) so bench.py can time the dominant kernel by itself */
+#define B200FA_FLAG_WORKSPACE_ZEROED 4u /* the caller zero-filled the workspace once (b200fa_workspace_init or cudaMemset) and
+                                          only b200fa calls have touched it since: skips the per-call cudaMemsetAsync of the
+                                          split-KV arrival counters (every call leaves them zero again) */
 
 /* status codes */
 #define B200FA_OK 0
@@ -71,7 +72,7 @@ int b200fa_version(void); /* major*10000 + minor*100 + patch */
  * scratch at flash-matrix.cu:223-224) and the stream.
  *
  * Dispatch (all on the GPU):
- *   n_q * (n_head/n_head_kv) <= 64  -> split-KV register-streaming kernel + combine (decode; HBM-bound)
+ *   n_q * (n_head/n_head_kv) <= 64  -> split-KV register-streaming kernel, splits merged in-kernel (decode; HBM-bound)
  *   otherwise, D == 128, f16 K/V    -> tcgen05/TMEM/TMA tile kernel (prefill; tensor-bound)
  *   otherwise                       -> the register-streaming kernel over 16-row groups
  * Requirements: D in {64, 128}; rows of q/k/v 16-byte aligned for f16/f32 (nb % 16 == 0), 2-byte for q8_0.
@@ -95,6 +96,9 @@ size_t b200fa_workspace_size(
     int q_type, int kv_type,
     int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
     int64_t ne11, int64_t ne12, int64_t ne13, uint32_t flags);
+
+/* cudaMemsetAsync(workspace, 0, bytes) on `stream`; see B200FA_FLAG_WORKSPACE_ZEROED. */
+int b200fa_workspace_init(void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
 
 /*
  * Sequence-split building blocks (cross-GPU split-KV).  Same maths as the reference's intra-GPU pair
@@ -120,7 +124,8 @@ int b200fa_flash_attn_partial(
     uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
 
 /* Merge n_parts partial triples per row (partials[p][n_rows][D+2], e.g. the all-gathered per-GPU
- * results) into dst[n_rows][D].  Replaces fa_reduce<128,nw> (flash_row_float.h:415-472). */
+ * results) into dst[n_rows][D].  Replaces fa_reduce<128,nw> (flash_row_float.h:415-472).  (Inside one GPU the
+ * split-KV kernel merges its own splits: the last CTA of a row group to finish does it.) */
 int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, int64_t D,
                           void* dst, int dst_type, b200fa_stream_t stream);
 
