@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         l.b200fa_quantize_q8_0.argtypes = [vp, C.c_int, vp, i64, vp]
         l.b200fa_dequantize_q8_0.restype = C.c_int
         l.b200fa_dequantize_q8_0.argtypes = [vp, vp, i64, vp]
+        l.b200fa_debug_timeline.restype = None
+        l.b200fa_debug_timeline.argtypes = [vp]
         _lib = l
     return _lib
 

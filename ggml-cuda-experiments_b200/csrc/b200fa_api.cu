@@ -3,9 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "decode_mma.cuh"
+#include "decode_stream.cuh"
 #include "prefill_tcgen05.cuh"
 #include "q8_0.cuh"
 
@@ -15,6 +17,7 @@ namespace {
 
 thread_local const char* g_last_dispatch = "none";
 thread_local int g_last_launches = 0;
+unsigned long long* g_timeline = nullptr;  // diagnostics: see b200fa_debug_timeline
 
 struct DeviceInfo {
     int sm_count = 0;
@@ -38,32 +41,94 @@ const DeviceInfo& device_info() {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Workspace layout: [arrival counters: fixed kCtrRegion bytes at offset 0][everything else].  The counter region is
+// the same for every shape, so B200FA_FLAG_WORKSPACE_ZEROED stays valid when calls of different shapes share a workspace.
+constexpr size_t kCtrRegion = 65536 * sizeof(unsigned int);
+
+enum PlanKind { kPrefill, kStream, kRows16 };
+
 struct Plan {
-    bool use_prefill = false;
+    PlanKind kind = kRows16;
+    // rows16 split-KV
     int n_splits = 1;
     int split_len = 0;
     int n_groups = 1;
-    size_t part_bytes = 0;   // split-KV partials
+    // stream-K decode
+    int cph = 0, n_units = 0, grid = 0, max_slots = 0, kv_end = 0;
+    long long total_chunks = 0;
+    size_t n_counters = 0;   // arrival counters needed (0 = none)
+    size_t part_bytes = 0;   // split-KV partials / stream-K records
     size_t qf16_bytes = 0;   // f16 copy of an f32 Q (tcgen05 path)
     size_t cls_bytes = 0;    // mask tile classes (tcgen05 path)
-    size_t ctr_bytes = 0;    // split-KV arrival counters (after the partials)
+    size_t ctr_bytes = 0;    // counter region actually reserved
     size_t total = 0;
 };
 
-Plan make_plan(int q_type, int kv_type, int64_t D, int64_t n_q, int64_t n_head, int64_t n_batch,
-               int64_t n_kv, int64_t n_head_kv, uint32_t flags, int sm_count, bool force_partial_out) {
+struct Shape {
+    int q_type, kv_type;
+    int64_t D, n_q, n_head, n_batch, n_kv, n_head_kv;
+    int64_t nb11, nb12, nb13, nb21, nb22, nb23;  // 0 = unknown (workspace sizing): assume the widest plan
+    const void* k; const void* v;
+    int64_t kv_pos0, n_kv_total;
+};
+
+bool stream_eligible(const Shape& sh, bool sizing) {
+    const int64_t rows = sh.n_q * (sh.n_head / sh.n_head_kv);
+    if (rows > 16 || (sh.D != 64 && sh.D != 128)) return false;
+    if (sh.n_head_kv * sh.n_batch > 65536) return false;
+    static const bool off = getenv("B200FA_DECODE_IMPL") && !strcmp(getenv("B200FA_DECODE_IMPL"), "rows16");
+    if (off) return false;
+    if (sizing || sh.kv_type == B200FA_TYPE_F16) return true;
+    // q8_0: the producer copies whole chunks of rows with 16-byte bulk copies -> rows must be contiguous and 16-byte aligned per head
+    const int64_t row = sh.D / kQ8BlockElems * kQ8BlockBytes;
+    if (sh.nb11 != row || sh.nb21 != row) return false;
+    return (((uintptr_t)sh.k | (uintptr_t)sh.v | (uintptr_t)sh.nb12 | (uintptr_t)sh.nb13 | (uintptr_t)sh.nb22 | (uintptr_t)sh.nb23) % 16) == 0;
+}
+
+Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial_out, bool sizing, bool allow_stream = true) {
     Plan pl;
+    const int64_t D = sh.D, n_q = sh.n_q, n_head = sh.n_head, n_batch = sh.n_batch, n_kv = sh.n_kv, n_head_kv = sh.n_head_kv;
     const int64_t gqa = n_head / n_head_kv;
     const int64_t rows = n_q * gqa;
-    pl.use_prefill = !force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D == 128 &&
-                     kv_type == B200FA_TYPE_F16 && n_q >= 64;
-    if (pl.use_prefill) {
-        if (q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * D * 2), 256);
+    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D == 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64) {
+        pl.kind = kPrefill;
+        if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * D * 2), 256);
         const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;
         pl.cls_bytes = align_up((size_t)(qt * kt), 256);
-        pl.total = pl.qf16_bytes + pl.cls_bytes;
+        pl.ctr_bytes = kCtrRegion;
+        pl.total = pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes;
         return pl;
     }
+    if (allow_stream && stream_eligible(sh, sizing)) {
+        pl.kind = kStream;
+        int64_t kv_end = n_kv;
+        if (flags & B200FA_FLAG_CAUSAL) {
+            const int64_t lim = n_q + (sh.n_kv_total - n_q) - sh.kv_pos0;  // keys < lim are visible to the last query
+            kv_end = lim < 0 ? 0 : (lim < n_kv ? lim : n_kv);
+        }
+        pl.kv_end = (int)kv_end;
+        pl.cph = (int)((kv_end + DK_CHUNK - 1) / DK_CHUNK);
+        if (pl.cph < 1) pl.cph = 1;
+        if (sizing) pl.cph = (int)((n_kv + DK_CHUNK - 1) / DK_CHUNK);  // the widest case
+        pl.n_units = (int)(n_head_kv * n_batch);
+        pl.total_chunks = (long long)pl.n_units * pl.cph;
+        int grid = sm_count;
+        if (const char* e = getenv("B200FA_STREAM_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
+        if (grid > DK_TAB) grid = DK_TAB;
+        pl.grid = (int)(pl.total_chunks < grid ? pl.total_chunks : grid);
+        const long long per = (pl.total_chunks + pl.grid - 1) / pl.grid;
+        pl.max_slots = (int)((per + pl.cph - 1) / pl.cph) + 1;
+        if (sizing) {  // cph (hence the slot count) shrinks under a causal clip: bound both extremes
+            const long long per1 = ((long long)pl.n_units + pl.grid - 1) / pl.grid;  // cph = 1
+            if (per1 + 1 > pl.max_slots) pl.max_slots = (int)per1 + 1;
+        }
+        pl.n_counters = (size_t)pl.n_units;
+        pl.part_bytes = align_up((size_t)(sizing ? sm_count : pl.grid) * pl.max_slots * DK_REC_ROWS * (size_t)(D + DK_REC_PAD) * 4, 256);
+        pl.ctr_bytes = kCtrRegion;
+        pl.total = pl.ctr_bytes + pl.part_bytes;
+        return pl;
+    }
+    pl.kind = kRows16;
     pl.n_groups = (int)((rows + kRows - 1) / kRows);
     const int64_t base = (int64_t)pl.n_groups * n_head_kv * n_batch;
     // Split planning: fill whole waves of resident CTAs (2 per SM).  Candidates keep >= 256 keys per split; pick
@@ -95,11 +160,13 @@ Plan make_plan(int q_type, int kv_type, int64_t D, int64_t n_q, int64_t n_head, 
     pl.split_len = (int)len;
     pl.n_splits = (int)((n_kv + len - 1) / len);
     if (pl.n_splits < 1) pl.n_splits = 1;
+    pl.ctr_bytes = kCtrRegion;
     if (pl.n_splits > 1) {
         pl.part_bytes = align_up((size_t)pl.n_splits * (size_t)(n_batch * n_q * n_head) * (size_t)(D + 2) * 4, 256);
-        pl.ctr_bytes = align_up((size_t)base * 4, 256);
+        pl.n_counters = (size_t)base;
+        if (pl.n_counters * 4 > kCtrRegion) pl.ctr_bytes = align_up(pl.n_counters * 4, 256);  // oversized: always memset
     }
-    pl.total = pl.part_bytes + pl.ctr_bytes;
+    pl.total = pl.ctr_bytes + pl.part_bytes;
     return pl;
 }
 
@@ -172,6 +239,41 @@ int launch_combine(const float* part, int n_parts, int64_t rows, void* dst, int 
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
+template <int D, int KV, int RH>
+int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t st) {
+    constexpr int smem = dk_smem_bytes<D, KV == B200FA_TYPE_Q8_0, RH>();
+    static thread_local bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
+        attr_set[dev] = true;
+    }
+    fa_decode_stream<D, KV, RH><<<grid, DK_THREADS, smem, st>>>(p, a, tk, tv);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
+    DkArgs a{};
+    a.cph = pl.cph; a.n_units = pl.n_units; a.total = pl.total_chunks; a.kv_end = pl.kv_end; a.max_slots = pl.max_slots;
+    a.counters = reinterpret_cast<unsigned int*>(ws);
+    a.rec = reinterpret_cast<float*>(ws + pl.ctr_bytes);
+    a.timeline = g_timeline;
+    a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
+    CUtensorMap tk{}, tv{};
+    if (p.kv_type == B200FA_TYPE_F16) {
+        if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.D)) return B200FA_ERR_CUDA;
+        if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.D)) return B200FA_ERR_CUDA;
+    }
+    const bool small = (int64_t)p.n_q * p.gqa <= 8;
+    const bool q8 = p.kv_type == B200FA_TYPE_Q8_0;
+    g_last_launches++;
+#define B200FA_STREAM(DD, KK) (small ? launch_stream_t<DD, KK, 1>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2>(p, a, pl.grid, tk, tv, st))
+    if (p.D == 128) return q8 ? B200FA_STREAM(128, B200FA_TYPE_Q8_0) : B200FA_STREAM(128, B200FA_TYPE_F16);
+    return q8 ? B200FA_STREAM(64, B200FA_TYPE_Q8_0) : B200FA_STREAM(64, B200FA_TYPE_F16);
+#undef B200FA_STREAM
+}
+
 }  // namespace
 
 extern "C" {
@@ -194,19 +296,24 @@ void b200fa_debug_set(void* timeout_word, float* dump, int dump_cta) {
     pf_debug().dump_cta = dump_cta;
 }
 const char* b200fa_last_dispatch(void) { return g_last_dispatch; }
+void b200fa_debug_timeline(void* stamps) { g_timeline = (unsigned long long*)stamps; }
 int b200fa_last_launch_count(void) { return g_last_launches; }
 
 size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
                              int64_t ne11, int64_t ne12, int64_t ne13, uint32_t flags) {
     const DeviceInfo& di = device_info();
     const int sms = di.ok ? di.sm_count : 148;
-    if (ne12 <= 0 || ne02 % ne12) return 0;
-    Plan a = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, sms, false);
-    Plan b = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, sms, true);  // _partial entry
-    Plan c = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags | B200FA_FLAG_NO_TCGEN05, sms, false);
+    if (ne12 <= 0 || ne02 % ne12 || ne00 <= 0 || ne01 <= 0 || ne03 <= 0 || ne11 <= 0) return 0;
     (void)ne13;
-    size_t m = a.total > b.total ? a.total : b.total;
-    if (c.total > m) m = c.total;
+    Shape sh{q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11};
+    size_t m = 0;
+    for (int variant = 0; variant < 5; variant++) {  // every path the two entry points can take for this shape
+        const bool partial = variant == 1 || variant == 3;
+        const bool stream = variant <= 1;
+        const uint32_t f = variant == 4 ? (flags | B200FA_FLAG_NO_TCGEN05) : flags;
+        const Plan pl = make_plan(sh, f, sms, partial, true, stream);
+        if (pl.total > m) m = pl.total;
+    }
     return m + 256;
 }
 
@@ -228,8 +335,10 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;  // sm_100a only, no fallback
 
     if (!(scale > 0.f)) flags |= B200FA_FLAG_NO_TCGEN05;  // the tile kernel takes row maxima of raw scores
-    Plan pl = make_plan(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, flags, di.sm_count, want_partial);
-    if (pl.total > 0 && (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256))) return B200FA_ERR_WORKSPACE;
+    Shape sh{q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total};
+    Plan pl = make_plan(sh, flags, di.sm_count, want_partial, false);
+    if (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256)) return B200FA_ERR_WORKSPACE;
+    char* ws = (char*)workspace;
 
     FaParams p{};
     p.q = (const char*)q; p.k = (const char*)k; p.v = (const char*)v; p.mask = (const char*)mask;
@@ -249,23 +358,27 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.total_rows = ne03 * ne01 * ne02;
     { static const int dm = getenv("B200FA_DBG_MODE") ? atoi(getenv("B200FA_DBG_MODE")) : 0; p.dbg_mode = dm; }
 
-    if (pl.use_prefill) {
+    if (pl.kind == kPrefill) {
         g_last_dispatch = "prefill_tcgen05";
         int launches = 0;
-        rc = launch_prefill_tcgen05(p, (char*)workspace, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
+        rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
         g_last_launches = launches;
         return rc;
     }
 
-    p.n_splits = pl.n_splits; p.split_len = pl.split_len;
     p.part_out = partial_out;
+    if (pl.n_counters > 0 && (!(flags & B200FA_FLAG_WORKSPACE_ZEROED) || pl.ctr_bytes != kCtrRegion)) {
+        if (cudaMemsetAsync(ws, 0, align_up(pl.n_counters * 4, 256), st) != cudaSuccess) return B200FA_ERR_CUDA;
+    }
+    if (pl.kind == kStream) {
+        g_last_dispatch = want_partial ? "decode_stream_partial" : "decode_stream";
+        return run_stream(p, pl, ws, st);
+    }
+    p.n_splits = pl.n_splits; p.split_len = pl.split_len;
     g_last_dispatch = want_partial ? "decode_splitkv_partial" : ((ne01 * p.gqa <= 64) ? "decode_splitkv" : "rows16_mma");
     if (pl.n_splits > 1) {
-        p.part = (float*)workspace;
-        p.counters = (unsigned int*)((char*)workspace + pl.part_bytes);
-        if (!(flags & B200FA_FLAG_WORKSPACE_ZEROED)) {
-            if (cudaMemsetAsync(p.counters, 0, pl.ctr_bytes, st) != cudaSuccess) return B200FA_ERR_CUDA;
-        }
+        p.counters = (unsigned int*)ws;
+        p.part = (float*)(ws + pl.ctr_bytes);
     }
     return run_rows16(p, pl, st);
 }

@@ -1,0 +1,611 @@
+// decode_stream.cuh — the bandwidth-bound decode path: a persistent, stream-K split-KV kernel whose K/V
+// bytes are moved by the TMA engine through a deep shared-memory ring.
+//
+// Replaces the reference's flash_attn_row<128,8,2,256> / flash_attn_row_fast (flash_row_float.h:4-413) AND
+// its fa_reduce<128,nw> (flash_row_float.h:415-472) for every call with n_q * (n_head / n_head_kv) <= 16 rows
+// per KV head (single-token decode of MHA/GQA models, short speculative bursts).
+//
+// Work decomposition ("stream-K"): a *unit* is one (kv head, batch) pair; its keys are cut into 64-key
+// chunks; all chunks of all units form one flat list that is divided evenly over the grid (one CTA per
+// SM).  A CTA therefore streams one contiguous run of chunks — possibly the tail of one unit, some whole
+// units and the head of another — and the HBM stream never stalls at a unit boundary.  Per unit segment the
+// CTA emits an (O~, m, l) record; the last CTA to finish a unit (arrival counter) merges the records,
+// which is the reference's fa_reduce algebra done in fp32.
+//
+// CTA = 8 consumer warps + 1 producer warp.
+//   producer (one elected lane): per chunk, waits for a free stage, then issues
+//       f16  : 2*D/64 cp.async.bulk.tensor loads (64 keys x 64 dims, 128B swizzle) from the ne/nb-strided tensors,
+//       q8_0 : two cp.async.bulk copies of the raw 34-byte blocks (rows must be contiguous),
+//       plus one 128-byte bulk copy per query row of the mask; all complete on the stage's mbarrier.
+//   consumers: chunk j belongs to warp group j & 1; warp (w & 3) of the group takes keys 16*(w&3)..+15 of it,
+//       reads its mma.sync fragments straight out of the swizzled stage (conflict-light 128-bit LDS), frees
+//       the stage, and does QK^T, online softmax and PV in registers — the same permuted-contraction
+//       fragment scheme as the rows16 kernel (decode_mma.cuh), so every lane touches 16 contiguous bytes.
+// q8_0: K block scales are applied in fp32 to per-block partial dot products (bit-equivalent to dotting
+// with f32(d)*q); V is dequantised to f16 = RN(d*q).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "decode_mma.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200fa {
+
+constexpr int DK_CHUNK = 64;   // keys per pipeline stage
+constexpr int DK_CWARPS = 8;   // consumer warps (two groups of four)
+constexpr int DK_THREADS = (DK_CWARPS + 1) * 32;
+constexpr int DK_SLOTS = DK_CWARPS;  // cross-warp merge slots: one per consumer warp
+constexpr int DK_MASK_BYTES = 16 * 128;
+constexpr int DK_REC_ROWS = 16;
+constexpr int DK_REC_PAD = 4;     // record rows are D + 4 floats (16-byte aligned): O~[D], m, l, 2 unused
+
+template <int D, bool Q8>
+struct DkGeom {
+    static constexpr int kRowBytes = Q8 ? D / 32 * kQ8BlockBytes : D * 2;
+    static constexpr int kBoxes = D / 64;                                    // 64-dim TMA boxes per K (or V) chunk
+    static constexpr int kKBytes = Q8 ? DK_CHUNK * kRowBytes : kBoxes * 8192;  // bytes of K (== V) per stage
+    static constexpr int kVOff = kKBytes;
+    static constexpr int kMaskOff = 2 * kKBytes;
+    static constexpr int kStageBytes = (2 * kKBytes + DK_MASK_BYTES + (Q8 ? 16 : 0) + 1023) / 1024 * 1024;
+};
+template <int D, int RH>
+struct DkMerge {
+    static constexpr int kFloatsPerLane = (D / 8) * 2 * RH + 2 * RH;  // O fragment + (m, l) per live row half
+    static constexpr int kSlotBytes = kFloatsPerLane * 32 * 4;
+    static constexpr int kBytes = DK_SLOTS * kSlotBytes;
+};
+constexpr int DK_TAB = 160;           // contributor table entries (>= SM count)
+constexpr int DK_TAIL_BYTES = 2 * 8 * 8 + 64 + DK_TAB * 4;  // barriers, flag, table
+constexpr int DK_SMEM_LIMIT = 227 * 1024;
+template <int D, bool Q8, int RH>
+__host__ __device__ constexpr int dk_stages() {
+    // As deep a ring as fits beside the merge slots, at most 8 — and EVEN: chunk j is consumed by warp group j & 1, and a
+    // stage must always be consumed by the same group, because an mbarrier waiter may never skip a phase (a group that
+    // only saw every other phase of a stage could find its parity already satisfied by the phase before).
+    int n = (DK_SMEM_LIMIT - 1024 - DK_TAIL_BYTES - DkMerge<D, RH>::kBytes) / DkGeom<D, Q8>::kStageBytes;
+    n = n > 8 ? 8 : n;
+    return n & ~1;
+}
+template <int D, bool Q8, int RH>
+__host__ __device__ constexpr int dk_smem_bytes() {
+    return dk_stages<D, Q8, RH>() * DkGeom<D, Q8>::kStageBytes + DkMerge<D, RH>::kBytes + DK_TAIL_BYTES + 1024;
+}
+
+struct DkArgs {
+    int cph;                 // chunks per unit
+    int n_units;             // n_head_kv * n_batch
+    long long total;         // n_units * cph
+    int kv_end;              // keys [0, kv_end) of every unit are streamed (n_kv, clipped by causality)
+    int max_slots;           // records a CTA may emit
+    float* rec;              // [grid][max_slots][DK_REC_ROWS][D + DK_REC_PAD]
+    unsigned int* counters;  // [n_units], zero between calls
+    int mask_bulk;           // mask rows can be staged with 128-byte bulk copies (16-byte aligned rows)
+    unsigned long long* timeline;  // diagnostics: 8 globaltimer stamps per CTA, or null
+};
+__device__ __forceinline__ unsigned long long dk_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+// 8 bytes at a 2-byte aligned shared address: three aligned words, funnel-shifted
+__device__ __forceinline__ uint2 lds_u8x8(uint32_t a) {
+    const uint32_t base = a & ~3u, sh = (a & 3u) << 3;
+    const uint32_t w0 = lds32(base), w1 = lds32(base + 4), w2 = lds32(base + 8);
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(DK_CWARPS * 32) : "memory"); }
+
+// owner CTA of flat chunk x when CTA c covers [c*T/G, (c+1)*T/G)
+__device__ __forceinline__ long long dk_owner(long long x, long long T, long long G) { return ((x + 1) * G - 1) / T; }
+
+template <int D, int KV_TYPE, int RH>
+__global__ void __launch_bounds__(DK_THREADS, 1)
+fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkArgs a,
+                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV) {
+    using namespace ptx;
+    static_assert(D == 64 || D == 128, "head size");
+    constexpr bool Q8 = (KV_TYPE == B200FA_TYPE_Q8_0);
+    using Geo = DkGeom<D, Q8>;
+    using Mrg = DkMerge<D, RH>;
+    constexpr int NS = dk_stages<D, Q8, RH>();
+    static_assert(NS >= 4 && NS % 2 == 0, "ring must be even (see dk_stages) and at least 4 deep");
+    constexpr int NC4 = D / 32;  // 16-byte chunks per lane per K row == q8_0 blocks per row
+    constexpr int NCV = D / 64;  // 64-wide halves of a V row
+    constexpr int NT = D / 8;    // output n-tiles
+    using Tile = KVTile<D, Q8>;
+
+    extern __shared__ uint8_t dk_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dk_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t stages_u32 = smem_u32(smem);
+    float* merge = reinterpret_cast<float*>(smem + NS * Geo::kStageBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Geo::kStageBytes + Mrg::kBytes);
+    uint64_t* empty = full + 8;
+    int* s_flag = reinterpret_cast<int*>(empty + 8);
+    int* s_tab = s_flag + 16;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long G = gridDim.x;
+    const long long start = (long long)blockIdx.x * a.total / G, stop = ((long long)blockIdx.x + 1) * a.total / G;
+    const int my_chunks = (int)(stop - start);
+
+    if (warp == DK_CWARPS) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+            fence_barrier_init();
+            if constexpr (!Q8) { prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); }
+        }
+        int pu = (int)(start / a.cph), pch = (int)(start - (long long)pu * a.cph);  // unit / chunk of the next issue
+        auto issue = [&](int i) {
+            const int u = pu, ch = pch;
+            if (++pch == a.cph) { pch = 0; pu++; }
+            const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv, ik3 = iq3 / p.rk3;
+            const int key0 = ch * DK_CHUNK;
+            const int stage = i % NS;
+            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes;
+            const bool whole = key0 + DK_CHUNK <= p.n_kv;
+            const int mrows = (a.mask_bulk && whole) ? p.n_q : 0;
+            if constexpr (!Q8) {
+                mbar_arrive_expect_tx(&full[stage], 2 * Geo::kKBytes + mrows * 128);
+#pragma unroll
+                for (int b = 0; b < Geo::kBoxes; b++) {
+                    tma_load_4d(smem + stage * Geo::kStageBytes + b * 8192, &tmK, &full[stage], 64 * b, key0, ik2, ik3);
+                    tma_load_4d(smem + stage * Geo::kStageBytes + Geo::kVOff + b * 8192, &tmV, &full[stage], 64 * b, key0, ik2, ik3);
+                }
+            } else {
+                const int rows = min(DK_CHUNK, p.n_kv - key0);
+                const uint32_t nbytes = (uint32_t)rows * Geo::kRowBytes, nb16 = nbytes & ~15u;
+                const char* ksrc = p.k + (int64_t)ik2 * p.nb12 + (int64_t)ik3 * p.nb13 + (int64_t)key0 * Geo::kRowBytes;
+                const char* vsrc = p.v + (int64_t)ik2 * p.nb22 + (int64_t)ik3 * p.nb23 + (int64_t)key0 * Geo::kRowBytes;
+                for (uint32_t o = nb16; o < nbytes; o += 4) {  // odd ragged tail: a few plain words
+                    *reinterpret_cast<uint32_t*>(smem + stage * Geo::kStageBytes + o) = __ldg(reinterpret_cast<const uint32_t*>(ksrc + o));
+                    *reinterpret_cast<uint32_t*>(smem + stage * Geo::kStageBytes + Geo::kVOff + o) = __ldg(reinterpret_cast<const uint32_t*>(vsrc + o));
+                }
+                mbar_arrive_expect_tx(&full[stage], 2 * nb16 + mrows * 128);
+                bulk_g2s(sb, ksrc, nb16, &full[stage]);
+                bulk_g2s(sb + Geo::kVOff, vsrc, nb16, &full[stage]);
+            }
+            for (int r = 0; r < mrows; r++)
+                bulk_g2s(sb + Geo::kMaskOff + r * 128, p.mask + (int64_t)r * p.nb31 + (int64_t)key0 * 2, 128, &full[stage]);
+        };
+        int i = 0;
+        if (lane == 0)
+            for (; i < min(NS, my_chunks); i++) issue(i);  // the ring starts filling before anyone else is ready
+        __syncthreads();
+        if (lane == 0) {
+            for (; i < my_chunks; i++) {
+                mbar_wait(&empty[i % NS], ((i / NS) & 1) ^ 1);
+                issue(i);
+            }
+        }
+        return;
+    }
+    __syncthreads();
+
+    // ===================== consumers =====================
+    const int g = lane >> 2, t = lane & 3;
+    const int group = warp >> 2, sub = warp & 3;
+    const int rows_total = p.n_q * p.gqa;
+    const bool mask_al8 = p.mask != nullptr && ((((uintptr_t)p.mask | (uintptr_t)p.nb31) & 7) == 0);
+
+    float o[NT][2 * RH];
+    float m_run[RH], l_run[RH];
+    uint32_t qa[NC4][RH][4];
+    int iq1r[RH], rq[RH];   // query position / q head within the GQA group of the lane's rows
+    bool rvalid[RH];
+    int lim[RH];
+    const char* mrow[RH];
+#pragma unroll
+    for (int h = 0; h < RH; h++) {
+        const int R = g + 8 * h;
+        rvalid[h] = R < rows_total;
+        iq1r[h] = (rvalid[h] ? R : 0) / p.gqa;
+        rq[h] = (rvalid[h] ? R : 0) % p.gqa;
+        const int64_t vis = p.causal ? (int64_t)iq1r[h] + p.causal_off - p.kv_pos0 + 1 : (int64_t)p.n_kv;
+        lim[h] = (int)max((int64_t)0, min((int64_t)a.kv_end, vis));
+        mrow[h] = p.mask ? p.mask + (int64_t)iq1r[h] * p.nb31 : nullptr;
+    }
+
+    // S = Q K^T (fp32) for the lane's 2 x 4 score slots
+    auto qk_tile = [&](const Tile& T, float (&s)[2][4]) {
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC4; c++) {
+                uint32_t k0, k1, k2, k3;
+                if constexpr (!Q8) {
+                    k0 = T.kf[nt][c][0]; k1 = T.kf[nt][c][1]; k2 = T.kf[nt][c][2]; k3 = T.kf[nt][c][3];
+                } else {
+                    q8x4_to_h2(T.kf[nt][c][0], k0, k1);
+                    q8x4_to_h2(T.kf[nt][c][1], k2, k3);
+                }
+                float acc0[4] = {0.f, 0.f, 0.f, 0.f};
+                float(&acc)[4] = Q8 ? acc0 : s[nt];
+                if constexpr (RH == 2) {
+                    mma_16816(acc, qa[c][0][0], qa[c][1][0], qa[c][0][1], qa[c][1][1], k0, k1);
+                    mma_16816(acc, qa[c][0][2], qa[c][1][2], qa[c][0][3], qa[c][1][3], k2, k3);
+                } else {
+                    mma_16816_top(acc[0], acc[1], qa[c][0][0], qa[c][0][1], k0, k1);
+                    mma_16816_top(acc[0], acc[1], qa[c][0][2], qa[c][0][3], k2, k3);
+                }
+                if constexpr (Q8) {
+                    const float d0 = h_bits_to_f(T.kd[2 * nt][c]), d1 = h_bits_to_f(T.kd[2 * nt + 1][c]);
+                    s[nt][0] += acc0[0] * d0; s[nt][1] += acc0[1] * d1;
+                    if constexpr (RH == 2) { s[nt][2] += acc0[2] * d0; s[nt][3] += acc0[3] * d1; }
+                }
+            }
+        }
+    };
+    // scale, mask, online softmax (lane holds keys kv0+4t+j, j=0..3, of its rows), then O += P V
+    auto softmax_pv_tile = [&](const Tile& T, const float (&s)[2][4], int kv0) {
+        float pr[RH][4];
+#pragma unroll
+        for (int h = 0; h < RH; h++) {
+            float tmax = -INFINITY;
+            float mv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.mask != nullptr) {
+                const float2 m01 = __half22float2(*reinterpret_cast<const __half2*>(&T.mk[h].x));
+                const float2 m23 = __half22float2(*reinterpret_cast<const __half2*>(&T.mk[h].y));
+                mv[0] = m01.x * kLog2e; mv[1] = m01.y * kLog2e; mv[2] = m23.x * kLog2e; mv[3] = m23.y * kLog2e;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int kv = kv0 + 4 * t + j;
+                float x = fmaf(s[j >> 1][2 * h + (j & 1)], p.scale_log2, mv[j]);
+                if (kv >= lim[h]) x = -INFINITY;
+                pr[h][j] = x;
+                tmax = fmaxf(tmax, x);
+            }
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+            const float m_new = fmaxf(m_run[h], tmax);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = fast_exp2(m_run[h] - m_use);  // m_run = -inf -> 0
+            float psum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                pr[h][j] = fast_exp2(pr[h][j] - m_use);
+                psum += pr[h][j];
+            }
+            l_run[h] = l_run[h] * alpha + psum;
+            m_run[h] = m_new;
+            if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+                for (int i = 0; i < NT; i++) { o[i][2 * h] *= alpha; o[i][2 * h + 1] *= alpha; }
+            }
+        }
+        const uint32_t pa0 = pack_half2(pr[0][0], pr[0][1]), pa2 = pack_half2(pr[0][2], pr[0][3]);
+        uint32_t pa1 = 0u, pa3 = 0u;
+        if constexpr (RH == 2) { pa1 = pack_half2(pr[1][0], pr[1][1]); pa3 = pack_half2(pr[1][2], pr[1][3]); }
+        // ---------- O += P V ----------
+#pragma unroll
+        for (int c = 0; c < NCV; c++) {
+            uint32_t vv[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if constexpr (!Q8) {
+                    vv[i][0] = T.vf[i][c][0]; vv[i][1] = T.vf[i][c][1]; vv[i][2] = T.vf[i][c][2]; vv[i][3] = T.vf[i][c][3];
+                } else {
+                    q8x4_to_h2(T.vf[i][c][0], vv[i][0], vv[i][1]);
+                    q8x4_to_h2(T.vf[i][c][1], vv[i][2], vv[i][3]);
+                    const __half2 d2 = __half2half2(__ushort_as_half(T.vd[i][c]));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        __half2 x = __hmul2(*reinterpret_cast<__half2*>(&vv[i][u]), d2);  // RN(d*q) per element
+                        vv[i][u] = *reinterpret_cast<uint32_t*>(&x);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+                const uint32_t b0 = prmt(vv[0][j >> 1], vv[1][j >> 1], sel);
+                const uint32_t b1 = prmt(vv[2][j >> 1], vv[3][j >> 1], sel);
+                if constexpr (RH == 2) mma_16816(o[c * 8 + j], pa0, pa1, pa2, pa3, b0, b1);
+                else mma_16816_top(o[c * 8 + j][0], o[c * 8 + j][1], pa0, pa2, b0, b1);
+            }
+        }
+    };
+
+    // Per-lane byte offsets into a stage, fixed for the whole kernel: every fragment load below is stage base + one of
+    // these + an immediate.  f16 stages are TMA boxes [64 keys][64 dims] with the 128-byte swizzle (16-byte chunk c of
+    // row r sits at chunk position c ^ (r & 7)); q8_0 stages are the raw 34-byte blocks, rows kRowBytes apart.
+    const int r0 = 16 * sub;
+    uint32_t kA[2][2], vA[4];   // f16: K rows rho(g) for n-tile nt / chunk parity; V rows 4t+i
+    uint32_t kB[2], kdB = 0, vB = 0, vdB = 0, vsh = 0;  // q8_0
+    if constexpr (!Q8) {
+        const int gb = (g >> 1) & 1, gp = g ^ (4 * (t & 1));
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            const int row = r0 + 4 * (g >> 1) + 2 * nt + (g & 1);
+            const int low = t ^ (2 * nt + (g & 1));
+#pragma unroll
+            for (int par = 0; par < 2; par++) kA[nt][par] = row * 128 + (((par ^ gb) * 4 + low) << 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) vA[i] = Geo::kVOff + (r0 + 4 * t + i) * 128 + ((gp ^ i) << 4);
+        kB[0] = kB[1] = 0;
+    } else {
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) kB[nt] = (r0 + 4 * (g >> 1) + 2 * nt + (g & 1)) * Geo::kRowBytes + 8 * t;
+        kdB = (r0 + 4 * t) * Geo::kRowBytes;
+        const uint32_t vl = (g >> 2) * kQ8BlockBytes + 2 + 8 * (g & 3);
+        vB = Geo::kVOff + kdB + (vl & ~3u);
+        vsh = (vl & 3u) << 3;
+        vdB = Geo::kVOff + kdB + (g >> 2) * kQ8BlockBytes;
+        kA[0][0] = kA[0][1] = kA[1][0] = kA[1][1] = 0; vA[0] = vA[1] = vA[2] = vA[3] = 0;
+    }
+
+    // fragments of one 16-key sub-tile out of a landed stage: K (+ K scales, mask) first, V once the scores are issued
+    auto read_k = [&](Tile& T, uint32_t sb, int kv0, bool staged_mask) {
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+#pragma unroll
+            for (int c = 0; c < NC4; c++) {
+                if constexpr (!Q8) {
+                    const uint4 x = lds128(sb + kA[nt][c & 1] + (c >> 1) * 8192);
+                    T.kf[nt][c][0] = x.x; T.kf[nt][c][1] = x.y; T.kf[nt][c][2] = x.z; T.kf[nt][c][3] = x.w;
+                } else if ((c & 1) == 0) {  // payload at 34c + 2: two bytes past a word boundary
+                    const uint32_t b = sb + kB[nt] + c * kQ8BlockBytes;
+                    const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8);
+                    T.kf[nt][c][0] = prmt(w0, w1, 0x5432); T.kf[nt][c][1] = prmt(w1, w2, 0x5432);
+                } else {                    // word aligned
+                    const uint32_t b = sb + kB[nt] + c * kQ8BlockBytes + 2;
+                    T.kf[nt][c][0] = lds32(b); T.kf[nt][c][1] = lds32(b + 4);
+                }
+            }
+        }
+        if constexpr (Q8) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int c = 0; c < NC4; c++) T.kd[i][c] = (uint16_t)lds_u16(sb + kdB + i * Geo::kRowBytes + c * kQ8BlockBytes);
+        }
+        if (p.mask != nullptr) {
+#pragma unroll
+            for (int h = 0; h < RH; h++) {
+                if (staged_mask) {
+                    T.mk[h] = lds64(sb + Geo::kMaskOff + iq1r[h] * 128 + (r0 + 4 * t) * 2);
+                } else if (mask_al8 && kv0 + 16 <= p.n_kv) {
+                    T.mk[h] = __ldg(reinterpret_cast<const uint2*>(mrow[h] + (int64_t)(kv0 + 4 * t) * 2));
+                } else {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) w[j] = (kv0 + 4 * t + j < p.n_kv) ? ld_u16(mrow[h] + (int64_t)(kv0 + 4 * t + j) * 2) : 0u;
+                    T.mk[h] = make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16));
+                }
+            }
+        }
+    };
+    auto read_v = [&](Tile& T, uint32_t sb, int kv0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int c = 0; c < NCV; c++) {
+                if constexpr (!Q8) {
+                    const uint4 x = lds128(sb + vA[i] + c * 8192);
+                    T.vf[i][c][0] = x.x; T.vf[i][c][1] = x.y; T.vf[i][c][2] = x.z; T.vf[i][c][3] = x.w;
+                } else {
+                    const uint32_t b = sb + vB + i * Geo::kRowBytes + c * 2 * kQ8BlockBytes;
+                    const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8);
+                    T.vf[i][c][0] = __funnelshift_r(w0, w1, vsh); T.vf[i][c][1] = __funnelshift_r(w1, w2, vsh);
+                    // rows past the end of the sequence hold stale bytes: a zero scale keeps them out of P.V
+                    const uint32_t d = lds_u16(sb + vdB + i * Geo::kRowBytes + c * 2 * kQ8BlockBytes);
+                    T.vd[i][c] = (kv0 + 4 * t + i < p.n_kv) ? (uint16_t)d : (uint16_t)0;
+                }
+            }
+        }
+    };
+
+    // Slot layout: [k][lane] floats.  k < KO: the lane's O fragment, k = (n-tile * 2*RH + e) with e = 2h + e1, which is
+    // row g + 8h, dim 64c + 16t + j + 8*e1 for n-tile c*8 + j;  k = KO + 2h / + 2h + 1: that row's m / l.
+    constexpr int KO = NT * 2 * RH, KPT = KO / DK_CWARPS;
+    auto slot_st = [&]() {
+        float* sp = merge + warp * (Mrg::kSlotBytes / 4) + lane;
+        int k = 0;
+#pragma unroll
+        for (int n = 0; n < NT; n++)
+#pragma unroll
+            for (int e = 0; e < 2 * RH; e++) sp[(k++) * 32] = o[n][e];
+#pragma unroll
+        for (int h = 0; h < RH; h++) { sp[(k++) * 32] = m_run[h]; sp[(k++) * 32] = l_run[h]; }
+    };
+    const bool stamp = a.timeline != nullptr && threadIdx.x == 0;
+    if (stamp) a.timeline[blockIdx.x * 8 + 0] = dk_now();
+
+    int i = 0, slot_idx = 0;
+    while (i < my_chunks) {
+        const long long x = start + i;
+        const int u = (int)(x / a.cph), ch0 = (int)(x - (long long)u * a.cph);
+        const int seg_end = min(my_chunks, i + (a.cph - ch0));
+        const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
+        // who else works on this unit (off the critical path: the segment's first stage is still in flight)
+        const long long c0 = dk_owner((long long)u * a.cph, a.total, G), c1 = dk_owner((long long)(u + 1) * a.cph - 1, a.total, G);
+        const int n_contrib = (int)(c1 - c0 + 1);
+
+        // ---- Q fragments of this unit's rows (f16; an f32 Q is rounded like the reference does, flash-llama.h:80) ----
+#pragma unroll
+        for (int h = 0; h < RH; h++) {
+            const char* qrow = p.q + (int64_t)iq1r[h] * p.nb01 + (int64_t)(ik2 * p.gqa + rq[h]) * p.nb02 + (int64_t)iq3 * p.nb03;
+#pragma unroll
+            for (int c = 0; c < NC4; c++) {
+                const int e0 = 8 * (t + 4 * c);
+                if (!rvalid[h]) {
+                    qa[c][h][0] = qa[c][h][1] = qa[c][h][2] = qa[c][h][3] = 0u;
+                } else if (p.q_type == B200FA_TYPE_F16) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(qrow + e0 * 2);
+                    qa[c][h][0] = v.x; qa[c][h][1] = v.y; qa[c][h][2] = v.z; qa[c][h][3] = v.w;
+                } else {
+                    const float4 v = *reinterpret_cast<const float4*>(qrow + e0 * 4);
+                    const float4 y = *reinterpret_cast<const float4*>(qrow + e0 * 4 + 16);
+                    qa[c][h][0] = pack_half2(v.x, v.y); qa[c][h][1] = pack_half2(v.z, v.w);
+                    qa[c][h][2] = pack_half2(y.x, y.y); qa[c][h][3] = pack_half2(y.z, y.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NT; n++)
+#pragma unroll
+            for (int e = 0; e < 2 * RH; e++) o[n][e] = 0.f;
+#pragma unroll
+        for (int h = 0; h < RH; h++) { m_run[h] = -INFINITY; l_run[h] = 0.f; }
+
+        // ---- this warp group's chunks of the segment ----
+        for (int j = i + ((group ^ i) & 1); j < seg_end; j += 2) {
+            const int key0 = (ch0 + (j - i)) * DK_CHUNK;
+            const int kv0 = key0 + 16 * sub;
+            const int stage = j % NS;
+            mbar_wait(&full[stage], (j / NS) & 1);
+            __syncwarp();
+            if (stamp && j == 0) a.timeline[blockIdx.x * 8 + 1] = dk_now();
+            Tile T;
+            float s[2][4];
+            const bool live = kv0 < a.kv_end;
+            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes;
+            if (live) {
+                read_k(T, sb, kv0, a.mask_bulk && key0 + DK_CHUNK <= p.n_kv);
+                qk_tile(T, s);
+                read_v(T, sb, kv0);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);  // fragments are in registers: hand the stage back
+            if (live) softmax_pv_tile(T, s, kv0);
+        }
+
+        // ---- fold the eight warps' partial states: every warp parks its (m, l, O) in its slot, then thread (lane, warp)
+        //      combines O elements [warp*KPT, +KPT) of that lane across the eight slots and stores them ----
+        if (stamp) a.timeline[blockIdx.x * 8 + 2] = dk_now();
+#pragma unroll
+        for (int h = 0; h < RH; h++) {
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+        }
+        bar_consumers();  // everyone is done reading the slots of the previous segment
+        slot_st();
+        bar_consumers();
+        {
+            float wgt[DK_CWARPS][RH], Ms[RH], Ls[RH];
+            const float* sl0 = merge + lane;
+#pragma unroll
+            for (int h = 0; h < RH; h++) {
+                float M = -INFINITY;
+#pragma unroll
+                for (int w = 0; w < DK_CWARPS; w++) M = fmaxf(M, sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h) * 32]);
+                const float Mu = (M == -INFINITY) ? 0.f : M;
+                float L = 0.f;
+#pragma unroll
+                for (int w = 0; w < DK_CWARPS; w++) {
+                    wgt[w][h] = fast_exp2(sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h) * 32] - Mu);
+                    L += sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h + 1) * 32] * wgt[w][h];
+                }
+                Ms[h] = M; Ls[h] = L;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KPT; kk++) {
+                const int k = warp * KPT + kk;
+                const int n = k / (2 * RH), e = k % (2 * RH), h = e >> 1, e1 = e & 1;
+                float acc = 0.f;
+#pragma unroll
+                for (int w = 0; w < DK_CWARPS; w++) acc += sl0[w * (Mrg::kSlotBytes / 4) + k * 32] * wgt[w][RH == 1 ? 0 : h];
+                const int R = g + 8 * h;
+                if (R >= rows_total) continue;
+                const int d = 64 * (n >> 3) + 16 * t + (n & 7) + 8 * e1;
+                const int64_t orow = ((int64_t)iq3 * p.n_q + iq1r[RH == 1 ? 0 : h]) * p.n_head + ik2 * p.gqa + rq[RH == 1 ? 0 : h];  // flash-llama.h:434
+                const float M = Ms[RH == 1 ? 0 : h], L = Ls[RH == 1 ? 0 : h];
+                const bool first = (n == 0 && e1 == 0 && t == 0);  // one thread per row also stores (m, l)
+                if (n_contrib > 1) {
+                    float* rec = a.rec + (((int64_t)blockIdx.x * a.max_slots + slot_idx) * DK_REC_ROWS + R) * (D + DK_REC_PAD);
+                    rec[d] = acc;
+                    if (first) { rec[D] = M; rec[D + 1] = L; }  // log2 units inside the kernel
+                } else if (p.dst != nullptr) {
+                    const float y = L > 0.f ? acc / L : 0.f;
+                    if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
+                    else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                } else {
+                    float* out = p.part_out + orow * (D + 2);
+                    out[d] = acc;
+                    if (first) { out[D] = M * kLn2; out[D + 1] = L; }
+                }
+            }
+        }
+        if (stamp) a.timeline[blockIdx.x * 8 + 3] = dk_now();
+        if (n_contrib > 1) {
+            // ---- the last CTA of this unit to arrive merges the records (fa_reduce, flash_row_float.h:415-472:
+            //      M = max m_i, L = sum l_i 2^(m_i-M), O = sum O~_i 2^(m_i-M) / L — one parallel fp32 pass) ----
+            __threadfence();
+            bar_consumers();
+            if (threadIdx.x == 0) {
+                const unsigned int old = atomicInc(a.counters + u, (unsigned int)n_contrib - 1);  // wraps to 0: self-resetting
+                *s_flag = (old == (unsigned int)n_contrib - 1);
+            }
+            for (int cc = threadIdx.x; cc < n_contrib; cc += DK_CWARPS * 32) {  // record slot of contributor c0 + cc
+                const long long st = (c0 + cc) * a.total / G;
+                s_tab[cc] = (int)(c0 + cc) * a.max_slots + (u - (int)(st / a.cph));
+            }
+            bar_consumers();
+            if (*s_flag != 0) {
+                __threadfence();
+                for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
+                    const int R = idx / D, d = idx % D;
+                    // one pass, loads batched eight records at a time (they are independent: one L2 round trip per batch)
+                    float M = -INFINITY, L = 0.f, acc = 0.f;
+                    for (int cb = 0; cb < n_contrib; cb += 8) {
+                        float mm[8], ll[8], aa[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const float* rec = a.rec + ((int64_t)s_tab[min(cb + e, n_contrib - 1)] * DK_REC_ROWS + R) * (D + DK_REC_PAD);
+                            mm[e] = __ldcg(rec + D); ll[e] = __ldcg(rec + D + 1); aa[e] = __ldcg(rec + d);
+                        }
+                        float Mb = M;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) if (cb + e < n_contrib) Mb = fmaxf(Mb, mm[e]);
+                        const float Mu = (Mb == -INFINITY) ? 0.f : Mb;
+                        const float w0 = fast_exp2(M - Mu);  // M = -inf -> 0
+                        L *= w0; acc *= w0;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            if (cb + e < n_contrib) {
+                                const float wt = fast_exp2(mm[e] - Mu);
+                                L += ll[e] * wt; acc += aa[e] * wt;
+                            }
+                        }
+                        M = Mb;
+                    }
+                    const int iq1 = R / p.gqa;
+                    const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
+                    if (p.dst != nullptr) {
+                        const float y = L > 0.f ? acc / L : 0.f;
+                        if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
+                        else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                    } else {
+                        float* out = p.part_out + orow * (D + 2);
+                        out[d] = acc;
+                        if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
+                    }
+                }
+            }
+        }
+        if (stamp) a.timeline[blockIdx.x * 8 + 4] = dk_now();
+        slot_idx++;
+        i = seg_end;
+    }
+}
+
+}  // namespace b200fa

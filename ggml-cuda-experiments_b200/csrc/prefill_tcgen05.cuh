@@ -183,7 +183,9 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
         const bool row_valid = qrow < p.n_q;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         const float c = p.scale_log2;
-        const char* mrow = (p.mask != nullptr && !p.causal && row_valid) ? p.mask + (int64_t)qrow * p.nb31 : nullptr;
+        // rows past n_q read the last real mask row (their results are never stored): every lane of a warp takes the
+        // same path, so the .sync.aligned tcgen05 instructions below always see a converged warp
+        const char* mrow = (p.mask != nullptr && !p.causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
         const bool mask_vec = (((uintptr_t)p.mask | (uintptr_t)p.nb31) & 15) == 0;
         const int64_t vis = p.causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
         const bool dumping = a.dump != nullptr && (int)blockIdx.x == a.dump_cta;
@@ -194,6 +196,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
             const int cls = pf_tile_class(p, a, qt, j);
             const int b = it & 1;
             mbar_wait(&sm.s_full[b], (it >> 1) & 1, a.dbg, 7);
+                __syncwarp();
             tc_fence_after();
             uint32_t s[4][32];
 #pragma unroll
@@ -237,6 +240,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                     }
                 }
             }
+            __syncwarp();
             // ---- row max (raw scores; scale > 0 on this path) ----
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -248,6 +252,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
             if (it > 0 && __any_sync(0xffffffffu, need)) {
                 // O currently holds sum_{tiles < it}; PV_{it-1} must have landed before we touch it
                 mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 8);
+                __syncwarp();
                 tc_fence_after();
                 const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.f;
                 l *= alpha;
@@ -289,6 +294,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
         const int64_t orow = ((int64_t)iq3 * p.n_q + qrow) * p.n_head + iq2;
         if (it > 0) {
             mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 9);
+                __syncwarp();
             tc_fence_after();
         }
         const float inv_l = l > 0.f ? 1.f / l : 0.f;
@@ -391,14 +397,14 @@ inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// f16 tensor [D=128][rows][heads][batch] with byte strides nb1..nb3; box = 64 x 128 x 1 x 1, 128B swizzle
+// f16 tensor [head_dim][rows][heads][batch] with byte strides nb1..nb3; box = 64 x box_rows x 1 x 1, 128B swizzle
 inline bool make_tile_map(CUtensorMap* m, const void* base, int64_t rows, int64_t heads, int64_t batch, int64_t nb1, int64_t nb2,
-                          int64_t nb3) {
+                          int64_t nb3, int box_rows = 128, int head_dim = PF_D) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
-    cuuint64_t dims[4] = {(cuuint64_t)PF_D, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
+    cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)nb1, (cuuint64_t)nb2, (cuuint64_t)nb3};
-    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -146,6 +146,9 @@ const char* b200fa_last_dispatch(void);
  * receives the first raw score tile, the unnormalised output tile and (l, m) of CTA `dump_cta`.  NULL disables. */
 void b200fa_debug_set(void* timeout_word, float* dump, int dump_cta);
 int b200fa_last_launch_count(void);
+/* Diagnostics for the stream decode kernel: `stamps` (device, 8 x uint64 per CTA) receives %globaltimer values at
+ * kernel start, first landed stage, end of streaming, after the in-CTA fold and at the end.  NULL disables. */
+void b200fa_debug_timeline(void* stamps);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Diagnostics: per-CTA %globaltimer stamps of the stream decode kernel (b200fa_debug_timeline).
+  python profiles/timeline.py --hq 32 --hk 32 --nkv 4096 [--q8] [--batch B]
+Prints, relative to the earliest CTA start: start, first landed stage, end of streaming, fold done, end (ns; min/median/max over CTAs)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from __graft_entry__ import load_package  # noqa: E402
+
+P = load_package()
+ap = argparse.ArgumentParser()
+ap.add_argument("--hq", type=int, default=32); ap.add_argument("--hk", type=int, default=32)
+ap.add_argument("--nkv", type=int, default=4096); ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--q8", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+D = 128
+k = (torch.rand((a.batch, a.hk, a.nkv, D), device=dev) * 2 - 1).half(); v = (torch.rand((a.batch, a.hk, a.nkv, D), device=dev) * 2 - 1).half()
+if a.q8:
+    k, v = P.quantize_q8_0(k), P.quantize_q8_0(v)
+q = torch.rand((a.batch, a.hq, 1, D), device=dev) * 2 - 1
+mask = torch.zeros((32, a.nkv), dtype=torch.float16, device=dev)
+stamps = torch.zeros((160, 8), dtype=torch.int64, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for it in range(3):
+    flush.fill_(it)  # evict K/V from L2
+    stamps.zero_()
+    P.lib().b200fa_debug_timeline(stamps.data_ptr())
+    P.flash_attn_ext(q, k, v, mask)
+    torch.cuda.synchronize()
+    P.lib().b200fa_debug_timeline(None)
+    s = stamps.cpu().numpy()
+    s = s[s[:, 0] > 0]
+    t0 = s[:, 0].min()
+    names = ["start", "first stage", "stream end", "fold done", "end"]
+    print(f"run {it}: {P.last_dispatch()} ctas={len(s)}")
+    for i, n in enumerate(names):
+        col = s[:, i] - t0
+        print(f"  {n:12s} min {col.min():7d}  med {int(np.median(col)):7d}  max {col.max():7d} ns")

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def test_c1_flash_matrix_case(mask_kind):
     Q, K, V = synth_qkv(128, 1, 256, 1, 1)
     run_both(Q, K, V, make_mask(mask_kind, 1, 256), mask_pad=32)
-    assert pkg().last_dispatch() == "decode_splitkv"
+    assert pkg().last_dispatch() == "decode_stream"
 
 
 @pytest.mark.parametrize("tag", ["c1_zero", "c1_tail", "c1_nomask", "llama_32h", "gqa_causal", "noise_mask", "d64"])
@@ -39,7 +39,7 @@ def test_against_reference_host_goldens(tag):
 def test_c2_llama7b_decode_kv4096_cache_view():
     Q, K, V = synth_qkv(128, 1, 4096, 32, 32)
     run_both(Q, K, V, make_mask("zeros", 1, 4096), cache_view=True, mask_pad=32)
-    assert pkg().last_dispatch() == "decode_splitkv"
+    assert pkg().last_dispatch() == "decode_stream"
     assert pkg().last_launch_count() == 1  # splits are merged in-kernel by the last CTA of each row group
 
 
@@ -228,3 +228,29 @@ def test_error_paths_on_device():
     with pytest.raises(P.B200FAError) as e:
         P.flash_attn_ext(to_dev(Q), to_dev(K), to_dev(V), workspace=Tiny())
     assert e.value.status == -3
+
+
+# ---- stream-K decomposition: CTAs whose chunk run crosses unit (kv head, batch) boundaries ----
+@pytest.mark.parametrize("n_kv,H,Hk,B", [(200, 32, 8, 40), (64, 8, 8, 3), (130, 16, 1, 5), (4096, 16, 1, 1), (1, 4, 2, 300)])
+def test_stream_units_cross_cta_boundaries(n_kv, H, Hk, B):
+    Q, K, V = synth_qkv(128, 1, n_kv, H, Hk, n_batch=B)
+    run_both(Q, K, V, make_mask("noise", 1, n_kv))
+    assert pkg().last_dispatch() == "decode_stream"
+    run_both(Q, K, V, None, dst_f16=True, q_f16=True)
+
+
+@pytest.mark.parametrize("n_kv,H,Hk,B", [(200, 32, 8, 40), (1000, 8, 2, 1), (62, 4, 4, 2), (63, 4, 4, 2), (1, 2, 2, 1)])
+def test_stream_q8_0_units_and_ragged_tails(n_kv, H, Hk, B):
+    Q, K, V = synth_qkv(128, 1, n_kv, H, Hk, n_batch=B)
+    run_both(Q, K, V, make_mask("noise", 1, n_kv), q8=True)
+    # heads whose byte size is not a multiple of 16 (odd n_kv) cannot be bulk-copied: those go to the rows16 kernel
+    assert pkg().last_dispatch() == ("decode_stream" if (n_kv * 136) % 16 == 0 or Hk * B == 1 else "decode_splitkv")
+
+
+def test_stream_head_dim_64_q8_and_f16():
+    Q, K, V = synth_qkv(64, 2, 777, 8, 2)
+    run_both(Q, K, V, make_mask("causal", 2, 777))
+    assert pkg().last_dispatch() == "decode_stream"
+    Q, K, V = synth_qkv(64, 2, 776, 8, 2)  # 776 * 68 bytes per head: a multiple of 16, so q8_0 heads can be bulk-copied
+    run_both(Q, K, V, None, q8=True)
+    assert pkg().last_dispatch() == "decode_stream"
