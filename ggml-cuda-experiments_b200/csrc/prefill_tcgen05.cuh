@@ -249,9 +249,14 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                 for (int i = 0; i < 32; i++) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[q4][i]));
             const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
             const bool need = m_tile > m_ref + PF_RESCALE_THRESHOLD;  // also true for the first finite max
+            // Every waiter must observe EVERY phase of an mbarrier in order (a parity wait that skips a phase is satisfied by
+            // the phase before it), so pv_done(it-1) is waited for in every iteration: here when O has to be rescaled,
+            // otherwise just before this tile's P is published.
+            bool saw_pv = false;
             if (it > 0 && __any_sync(0xffffffffu, need)) {
                 // O currently holds sum_{tiles < it}; PV_{it-1} must have landed before we touch it
                 mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 8);
+                saw_pv = true;
                 __syncwarp();
                 tc_fence_after();
                 const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.f;
@@ -285,6 +290,10 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                 tmem_st32(trow + PF_TM_S + 128u * b + 32u * h, pk);
             }
             l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            if (it > 0 && !saw_pv) {
+                mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 10);
+                __syncwarp();
+            }
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sm.p_full[b]);
