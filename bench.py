@@ -253,8 +253,12 @@ def main():
     # per-call counter memset skipped (workspace contract B200FA_FLAG_WORKSPACE_ZEROED) so only the kernel is in the graph
     k_local, k_ms = time_steps(lambda i: c2["step"](i, P.FLAG_WORKSPACE_ZEROED), min(args.steps, 2000), warmup)
     achieved = c2["bytes"] / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fa_rows16_splitkv<128,f16>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "kernel_us": k_ms * 1e3,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("c2_fa_decode_stream")
+    roofline = {"bound": "hbm", "kernel": "fa_decode_stream<128,f16,1>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src, "kernel_us": k_ms * 1e3,
                 "algorithmic_bytes_per_launch": c2["bytes"], "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # ---------------------------------------------------------------- e2e: host buffers through the ABI, copies inside the timed region
@@ -309,6 +313,26 @@ def main():
                          "frac_of_measured_bf16_peak": tf / peaks["bf16_tflops"], "frac_of_nominal_2250": tf / 2250.0}
         out["config"] = "c3: LLaMA-7B prefill, 32 heads, d=128, 2048x2048 causal f16 Q/K/V, f32 out (BASELINE.json configs[2]); causal FLOPs 34.36 G"
         return out
+
+    def run_c2_32k():
+        H, n_kv = 32, 32768
+        nsets = 2
+        ks = [rand_f16((1, n_kv, H, D), 110 + s).permute(0, 2, 1, 3) for s in range(nsets)]
+        vs = [rand_f16((1, n_kv, H, D), 120 + s).permute(0, 2, 1, 3) for s in range(nsets)]
+        q = (torch.rand((1, 1, H, D), device=dev) * 2 - 1).permute(0, 2, 1, 3)
+        mask = torch.zeros((32, n_kv), dtype=torch.float16, device=dev)
+        dst = torch.empty((1, 1, H, D), dtype=torch.float32, device=dev)
+        ws = P.Workspace(P.workspace_size(P.TYPE_F32, P.TYPE_F16, D, 1, H, 1, n_kv, H, 1))
+        nbytes = 2 * H * n_kv * D * 2
+        def step(i):
+            P.flash_attn_ext(q, ks[i % nsets], vs[i % nsets], mask, dst=dst, flags=P.FLAG_WORKSPACE_ZEROED, workspace=ws)
+        step(0); torch.cuda.synchronize()
+        nl = P.last_launch_count(); disp = P.last_dispatch()
+        _, t = time_steps(step, 200, 5, chunk=50)
+        return {"config": "LLaMA-7B decode at 32K KV: 32 heads, d=128, batch 1, f16 + mask, KV-cache view strides (north_star's >= 80 % HBM target shape)",
+                "gbps": nbytes / (t * 1e-3) / 1e9, "us_per_step": t * 1e3, "frac_of_measured_hbm": nbytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "frac_of_nominal_8TBs": nbytes / (t * 1e-3) / 1e9 / 8000.0, "kv_bytes": nbytes, "launches_per_step": nl, "dispatch": disp,
+                "l2": f"{nsets} rotating K/V sets of {nbytes / 1e6:.0f} MB"}
 
     def run_c4():
         Hq, Hk, B, n_kv = 32, 8, 64, 8192
@@ -377,7 +401,7 @@ def main():
                 "l2": f"{nsets} rotating q8_0 K/V sets of {per_gpu / 1e6:.0f} MB per GPU"}
 
     if not (args.quick or args.no_extras):
-        for name, fn in (("c3_prefill", run_c3), ("c4_gqa_decode", run_c4), ("c5_q8_0_split_kv", run_c5)):
+        for name, fn in (("c2_decode_32k_kv", run_c2_32k), ("c3_prefill", run_c3), ("c4_gqa_decode", run_c4), ("c5_q8_0_split_kv", run_c5)):
             try:
                 results[name] = fn()
             except Exception as e:  # noqa: BLE001
