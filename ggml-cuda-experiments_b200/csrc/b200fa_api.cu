@@ -90,7 +90,8 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     const int64_t D = sh.D, n_q = sh.n_q, n_head = sh.n_head, n_batch = sh.n_batch, n_kv = sh.n_kv, n_head_kv = sh.n_head_kv;
     const int64_t gqa = n_head / n_head_kv;
     const int64_t rows = n_q * gqa;
-    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D == 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64) {
+    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D == 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64 &&
+        n_kv <= (int64_t)PF_MAX_KV_TILES * PF_BN) {
         pl.kind = kPrefill;
         if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * D * 2), 256);
         const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;

@@ -1,21 +1,28 @@
 // prefill_tcgen05.cuh — the tensor-bound prefill path: QK^T and P·V as tcgen05.mma tiles accumulating in
-// TMEM, K/V streamed by TMA through an mbarrier pipeline, online softmax one thread per query row.
+// TMEM, K/V streamed by TMA through an mbarrier ring, online softmax one thread per query row.
 //
 // Replaces the reference's flash_attn_ext_f16<128,16,128> (flash-llama.h:5-438; WMMA 16x16x16, f16
 // accumulators, per-warp K/V fragment loads from global, smem round-trips per S tile).
 //
-// CTA = one 128-row query tile of one head (M = 128).  192 threads:
-//   warps 0-3  softmax + correction + epilogue: thread r owns query row r (TMEM lane r), so row max / sum
-//              need no shuffles at all;
-//   warp  4    TMA producer (one elected lane): Q once, then K_j / V_j tiles into a 2-stage ring;
-//   warp  5    MMA issuer (one elected lane): S_j = Q K_j^T (SS, both K-major), O += P_j V_j (TS: P from
-//              TMEM, V MN-major from smem).
-// TMEM (512 columns): S0 [0,128) S1 [128,256) O [256,384).  P_j (f16) overwrites the first 64 columns
-// of its S buffer.  S is double-buffered so S_{j+1} is computed while the softmax of tile j runs.
-// O is rescaled lazily: only when a row max grows by more than 2^8 (P stays within f16 range).
-// KV tiles are classified full / mixed / skip — from the causal flag arithmetically, or from a one-pass
-// scan of the mask tensor (the reference detects all -inf blocks at run time, flash-llama.h:276-278) —
-// so the mask is only read on mixed (diagonal) tiles and masked tiles cost nothing.
+// CTA = TWO 128-row query tiles of one head (256 query rows) sharing every K/V tile: the per-SM L2->smem
+// traffic per tensor-core cycle is half that of a one-tile CTA (which would need more than the chip's L2
+// bandwidth at full tensor rate), and while one tile's softmax runs the tensor pipe works on the other.
+// 384 threads:
+//   warps 0-3   softmax / lazy correction / epilogue of tile 0: thread r owns query row r (TMEM lane r), so row
+//               max / sum need no shuffles at all;
+//   warps 4-7   the same for tile 1;
+//   warp  8     TMA producer (one elected lane): Q0, Q1 once, then K_j / V_j tiles into a 2-stage ring;
+//   warp  9     MMA issuer (one elected lane): S_t = Q_t K_j^T (SS, both K-major), O_t += P_t V_j (TS: P from
+//               TMEM, V MN-major from smem), ordered  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  so each softmax group
+//               has a full tile's worth of tensor work to hide behind;
+//   warps 10-11 idle (they complete the third warpgroup, which gives its registers to the softmax warpgroups
+//               with setmaxnreg).
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).  P_t (f16) overwrites the first 64
+// columns of S_t.  O is rescaled lazily: only when a row max grows by more than 2^8 (P stays within f16 range).
+// KV tiles are classified full / mixed / skip per 128x128 tile — from the causal flag arithmetically, or from
+// a one-pass scan of the mask tensor (the reference detects all -inf blocks at run time,
+// flash-llama.h:276-278) — so the mask is only read on mixed (diagonal) tiles and masked tiles cost nothing.
+// Rule kept throughout: every waiter of an mbarrier observes every phase of it, in order.
 #pragma once
 #include <cuda.h>
 
@@ -25,33 +32,39 @@
 namespace b200fa {
 
 constexpr int PF_BM = 128, PF_BN = 128, PF_D = 128;
-constexpr int PF_THREADS = 192;
+constexpr int PF_THREADS = 384;
 constexpr uint32_t PF_TILE_BYTES = 128 * 128 * 2;  // one 128x128 f16 tile
 constexpr uint32_t PF_TMEM_COLS = 512;
-constexpr uint32_t PF_TM_S = 0, PF_TM_O = 256;     // S buffer b at PF_TM_S + 128*b
+constexpr uint32_t PF_TM_S = 0, PF_TM_O = 256;     // tile t: S at PF_TM_S + 128*t, O at PF_TM_O + 128*t
 constexpr float PF_RESCALE_THRESHOLD = 8.0f;       // log2 units
+constexpr int PF_REGS_SOFTMAX = 216, PF_REGS_OTHER = 40;
+constexpr int PF_STAGGER_CYCLES = 1100;
+constexpr int PF_MAX_KV_TILES = 4096;              // schedule capacity: n_kv <= 524288 on this path
 
 struct __align__(1024) PfShared {
-    uint8_t q[PF_TILE_BYTES];     // [2 k-blocks][128 rows][64 d]  128B-swizzled, K-major
-    uint8_t k[2][PF_TILE_BYTES];  // same layout, rows = keys
-    uint8_t v[2][PF_TILE_BYTES];  // [2 d-halves][128 keys][64 d]  128B-swizzled, MN-major B operand
-    uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done;
+    uint8_t q[2][PF_TILE_BYTES];  // per Q tile: [2 k-blocks][128 rows][64 d]  128B-swizzled, K-major
+    uint8_t k[2][PF_TILE_BYTES];  // ring stage: same layout, rows = keys
+    uint8_t v[2][PF_TILE_BYTES];  // ring stage: [2 d-halves][128 keys][64 d]  128B-swizzled, MN-major B operand
+    uint64_t q_full[2], k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done[2];
     uint32_t tmem_base;
+    int j_lo, j_hi;               // KV tiles outside [j_lo, j_hi) are invisible to both query tiles
+    uint8_t cls2[PF_MAX_KV_TILES];  // per KV tile: class for query tile 0 (bits 0-1) and 1 (bits 2-3)
 };
 
 struct PfArgs {
-    const uint8_t* cls;        // [n_q_tiles][n_kv_tiles] tile classes from the mask scan, or null
-    int n_q_tiles, n_kv_tiles;
+    const uint8_t* cls;        // [n_q_tiles][n_kv_tiles] 128x128 tile classes from the mask scan, or null
+    int n_q_tiles, n_kv_tiles; // 128-row / 128-key tiles
+    int n_q_pairs;             // CTAs per (head, batch)
     float inv_scale;           // 1/scale (mask values are folded into raw scores)
     unsigned long long* dbg;   // timeout codes (mapped host memory), may be null
-    float* dump;               // diagnostics: S of the first tile + final O of CTA `dump_cta`, may be null
+    float* dump;               // diagnostics, may be null
     int dump_cta;
 };
 
-// 0 = every element visible, 1 = mixed (mask / causal edge / ragged tail), 2 = nothing visible
+// 0 = every element visible, 1 = mixed (mask / causal edge / ragged tail), 2 = nothing visible.  qt = 128-row tile index.
 __device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j) {
     const int kv0 = j * PF_BN;
-    if (kv0 >= p.n_kv) return 2;
+    if (kv0 >= p.n_kv || qt >= a.n_q_tiles) return 2;
     int c = (kv0 + PF_BN > p.n_kv) ? 1 : 0;
     if (p.causal) {
         const int64_t q0 = (int64_t)qt * PF_BM;
@@ -68,11 +81,39 @@ __device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a,
     }
     return c;
 }
+// next KV tile >= j that tile qt needs, or -1
 __device__ __forceinline__ int pf_next_tile(const FaParams& p, const PfArgs& a, int qt, int j) {
     for (; j < a.n_kv_tiles; j++)
         if (pf_tile_class(p, a, qt, j) != 2) return j;
     return -1;
 }
+// next KV tile >= j that either query tile of the pair needs, or -1
+__device__ __forceinline__ int pf_next_union(const FaParams& p, const PfArgs& a, int qt0, int j) {
+    for (; j < a.n_kv_tiles; j++)
+        if (pf_tile_class(p, a, qt0, j) != 2 || pf_tile_class(p, a, qt0 + 1, j) != 2) return j;
+    return -1;
+}
+
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __global__ void __launch_bounds__(PF_THREADS, 1)
 fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ PfArgs a,
@@ -83,25 +124,26 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
     PfShared& sm = *reinterpret_cast<PfShared*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // heavy (late) query tiles first: under a causal mask tile qt costs qt+1 KV tiles
-    const int per_tile = p.n_head * p.n_batch;
-    const int qt = a.n_q_tiles - 1 - (int)(blockIdx.x / per_tile);
-    const int iq2 = (int)(blockIdx.x % per_tile) % p.n_head;
-    const int iq3 = (int)(blockIdx.x % per_tile) / p.n_head;
+    // heavy (late) query tile pairs first: under a causal mask pair qp costs ~ 4*qp + 3 tile products
+    const int per_pair = p.n_head * p.n_batch;
+    const int qp = a.n_q_pairs - 1 - (int)(blockIdx.x / per_pair);
+    const int iq2 = (int)(blockIdx.x % per_pair) % p.n_head;
+    const int iq3 = (int)(blockIdx.x % per_pair) / p.n_head;
     const int ik2 = iq2 / p.gqa, ik3 = iq3 / p.rk3;
-    const int q0 = qt * PF_BM;
+    const int qt0 = 2 * qp;  // 128-row tiles qt0 and qt0 + 1
 
     if (threadIdx.x == 0) {
-        mbar_init(&sm.q_full, 1);
         for (int s = 0; s < 2; s++) {
-            mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
-            mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
-            mbar_init(&sm.s_full[s], 1); mbar_init(&sm.p_full[s], 128);
+            mbar_init(&sm.q_full[s], 1);
+            mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 2);  // one arrival per MMA issuer
+            mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 2);
+            mbar_init(&sm.s_full[s], 1); mbar_init(&sm.p_full[s], 4);  // one arrival per softmax warp
+            mbar_init(&sm.pv_done[s], 1);
         }
-        mbar_init(&sm.pv_done, 1);
         fence_barrier_init();
+        sm.j_lo = a.n_kv_tiles; sm.j_hi = 0;
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc(&sm.tmem_base, PF_TMEM_COLS);
         tmem_relinquish();
     }
@@ -110,106 +152,168 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
-            mbar_arrive_expect_tx(&sm.q_full, PF_TILE_BYTES);
-            tma_load_4d(sm.q, &tmQ, &sm.q_full, 0, q0, iq2, iq3);
-            tma_load_4d(sm.q + PF_TILE_BYTES / 2, &tmQ, &sm.q_full, 64, q0, iq2, iq3);
-            int it = 0;
-            for (int j = pf_next_tile(p, a, qt, 0); j >= 0; j = pf_next_tile(p, a, qt, j + 1), it++) {
-                const int st = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&sm.k_empty[st], ph ^ 1, a.dbg, 1);
-                mbar_arrive_expect_tx(&sm.k_full[st], PF_TILE_BYTES);
-                tma_load_4d(sm.k[st], &tmK, &sm.k_full[st], 0, j * PF_BN, ik2, ik3);
-                tma_load_4d(sm.k[st] + PF_TILE_BYTES / 2, &tmK, &sm.k_full[st], 64, j * PF_BN, ik2, ik3);
-                mbar_wait(&sm.v_empty[st], ph ^ 1, a.dbg, 2);
-                mbar_arrive_expect_tx(&sm.v_full[st], PF_TILE_BYTES);
-                tma_load_4d(sm.v[st], &tmV, &sm.v_full[st], 0, j * PF_BN, ik2, ik3);
-                tma_load_4d(sm.v[st] + PF_TILE_BYTES / 2, &tmV, &sm.v_full[st], 64, j * PF_BN, ik2, ik3);
-            }
+    // ---- the CTA's schedule, once: class of KV tile j for query tile qt0 (bits 0-1) and qt0+1 (bits 2-3), and the
+    //      range [j_lo, j_hi) outside which nothing is visible.  Every role then walks the same list with cheap LDS. ----
+    {
+        int lo = a.n_kv_tiles, hi = 0;
+        for (int j = threadIdx.x; j < a.n_kv_tiles; j += PF_THREADS) {
+            const int c = pf_tile_class(p, a, qt0, j) | (pf_tile_class(p, a, qt0 + 1, j) << 2);
+            sm.cls2[j] = (uint8_t)c;
+            if (c != 0xA) { lo = min(lo, j); hi = max(hi, j + 1); }
         }
-    } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, PF_BN, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc_f16(PF_BM, PF_D, 0, 1);
-            const uint32_t q_addr = smem_u32(sm.q);
-            auto issue_qk = [&](int it_s) {
-                const int st = it_s & 1;
-                mbar_wait(&sm.k_full[st], (it_s >> 1) & 1, a.dbg, 3);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(sm.k[st]);
-                const uint32_t d_tmem = tmem + PF_TM_S + 128u * (it_s & 1);
+        if (hi > 0) { atomicMin(&sm.j_lo, lo); atomicMax(&sm.j_hi, hi); }
+    }
+    __syncthreads();
+    const int j_lo = sm.j_lo, j_hi = sm.j_hi;
+
+    if (warp >= 8) {
+        reg_dec<PF_REGS_OTHER>();
+        if (warp == 8) {
+            // ===================== TMA producer =====================
+            if (elect_one()) {
+                prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++) {
-                    const uint32_t off = (ks >> 2) * (PF_TILE_BYTES / 2) + (ks & 3) * 32;
-                    mma_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
-                           idesc_qk, ks > 0);
+                for (int t = 0; t < 2; t++) {
+                    if (qt0 + t >= a.n_q_tiles) continue;
+                    mbar_arrive_expect_tx(&sm.q_full[t], PF_TILE_BYTES);
+                    tma_load_4d(sm.q[t], &tmQ, &sm.q_full[t], 0, (qt0 + t) * PF_BM, iq2, iq3);
+                    tma_load_4d(sm.q[t] + PF_TILE_BYTES / 2, &tmQ, &sm.q_full[t], 64, (qt0 + t) * PF_BM, iq2, iq3);
                 }
-                tc_commit(&sm.k_empty[st]);
-                tc_commit(&sm.s_full[it_s & 1]);
-            };
-            mbar_wait(&sm.q_full, 0, a.dbg, 4);
-            int it = 0;
-            int j = pf_next_tile(p, a, qt, 0);
-            if (j >= 0) issue_qk(0);
-            while (j >= 0) {
-                const int jn = pf_next_tile(p, a, qt, j + 1);
-                if (jn >= 0) issue_qk(it + 1);  // S_{it+1} runs on the tensor pipe while softmax(it) is in flight
-                const int b = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&sm.p_full[b], ph, a.dbg, 5);
-                mbar_wait(&sm.v_full[b], ph, a.dbg, 6);
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(sm.v[b]);
-                const uint32_t p_tmem = tmem + PF_TM_S + 128u * b;
+                int u = 0;
+                for (int j = j_lo; j < j_hi; j++) {
+                    if (sm.cls2[j] == 0xA) continue;
+                    const int st = u & 1;
+                    const uint32_t ph = (u >> 1) & 1;
+                    mbar_wait(&sm.k_empty[st], ph ^ 1, a.dbg, 1);
+                    mbar_arrive_expect_tx(&sm.k_full[st], PF_TILE_BYTES);
+                    tma_load_4d(sm.k[st], &tmK, &sm.k_full[st], 0, j * PF_BN, ik2, ik3);
+                    tma_load_4d(sm.k[st] + PF_TILE_BYTES / 2, &tmK, &sm.k_full[st], 64, j * PF_BN, ik2, ik3);
+                    mbar_wait(&sm.v_empty[st], ph ^ 1, a.dbg, 2);
+                    mbar_arrive_expect_tx(&sm.v_full[st], PF_TILE_BYTES);
+                    tma_load_4d(sm.v[st], &tmV, &sm.v_full[st], 0, j * PF_BN, ik2, ik3);
+                    tma_load_4d(sm.v[st] + PF_TILE_BYTES / 2, &tmV, &sm.v_full[st], 64, j * PF_BN, ik2, ik3);
+                    u++;
+                }
+            }
+        } else if (warp <= 10) {
+            // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 query tile 1 =====================
+            // tcgen05.mma issue blocks while the tensor pipe's short queue is full, so any scalar work between two batches
+            // of one issuer is tensor idle time — unless the other issuer's batch is queued behind it.  Each issuer is ONE
+            // elected thread running a lean loop:  PV_t(previous tile), QK_t(this tile), per KV tile of the schedule.
+            const int t = warp - 9;
+            if (elect_one()) {
+                constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, PF_BN, 0, 0);
+                constexpr uint32_t idesc_pv = make_idesc_f16(PF_BM, PF_D, 0, 1);
+                const uint64_t dq = make_smem_desc_sw128(smem_u32(sm.q[t]), 16, 1024);
+                const uint64_t dk[2] = {make_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), make_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024)};
+                const uint64_t dv[2] = {make_smem_desc_sw128(smem_u32(sm.v[0]), PF_TILE_BYTES / 2, 1024),
+                                        make_smem_desc_sw128(smem_u32(sm.v[1]), PF_TILE_BYTES / 2, 1024)};
+                const uint32_t tS = tmem + PF_TM_S + 128u * t, tO = tmem + PF_TM_O + 128u * t;
+                int n_pv = 0;      // products issued so far = phase counter of p_full[t]
+                int pend = -1;     // stage whose V the pending P.V needs, or -1
+                bool have_q = false;
+                auto flush_pv = [&]() {
+                    mbar_wait(&sm.p_full[t], n_pv & 1, a.dbg, 5);
+                    tc_fence_after();
+                    if (n_pv == 0) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++)
-                    mma_ts(tmem + PF_TM_O, p_tmem + ks * 8, make_smem_desc_sw128(v_addr + ks * 2048, PF_TILE_BYTES / 2, 1024),
-                           idesc_pv, (it > 0 || ks > 0) ? 1u : 0u);
-                tc_commit(&sm.v_empty[b]);
-                tc_commit(&sm.pv_done);
-                j = jn;
-                it++;
+                        for (int ks = 0; ks < 8; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, ks > 0);
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, 1u);
+                    }
+                    tc_commit(&sm.pv_done[t]);
+                    tc_commit(&sm.v_empty[pend]);
+                    n_pv++;
+                    pend = -1;
+                };
+                if (t == 1 && j_lo < j_hi && (sm.cls2[j_lo] & 3) != 2) {
+                    // Stagger the two tiles by about half a period so that one tile's softmax runs while the tensor pipe works
+                    // for the other from the first iteration on (left alone they only drift apart after ~6 iterations).
+                    // A one-shot wait on phase 0 of the other tile's barrier is safe: that phase cannot be followed by another
+                    // complete one before this thread has looked (the next one needs a whole softmax first).
+                    mbar_wait(&sm.s_full[0], 0, a.dbg, 11);
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < PF_STAGGER_CYCLES) {}
+                }
+                int u = 0;
+                for (int j = j_lo; j < j_hi; j++) {
+                    const int c2 = sm.cls2[j];
+                    if (c2 == 0xA) continue;
+                    const bool active = ((c2 >> (2 * t)) & 3) != 2;
+                    const int st = u & 1;
+                    const uint32_t ph = (u >> 1) & 1;
+                    if (pend >= 0) flush_pv();  // always before waiting on a later stage: the producer needs v_empty to move on
+                    mbar_wait(&sm.k_full[st], ph, a.dbg, 3);
+                    if (active) {
+                        if (!have_q) { mbar_wait(&sm.q_full[t], 0, a.dbg, 4); have_q = true; }
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++) {
+                            const uint64_t off = (uint64_t)(((ks >> 2) * (PF_TILE_BYTES / 2) + (ks & 3) * 32) >> 4);
+                            mma_ss(tS, dq + off, dk[st] + off, idesc_qk, ks > 0);
+                        }
+                        tc_commit(&sm.s_full[t]);
+                        tc_commit(&sm.k_empty[st]);
+                    } else {
+                        mbar_arrive(&sm.k_empty[st]);
+                    }
+                    mbar_wait(&sm.v_full[st], ph, a.dbg, 6);
+                    if (active) pend = st;
+                    else mbar_arrive(&sm.v_empty[st]);
+                    u++;
+                }
+                if (pend >= 0) flush_pv();
             }
         }
     } else {
         // ===================== softmax / correction / epilogue: thread = query row =====================
-        const int r = threadIdx.x;  // 0..127
+        reg_inc<PF_REGS_SOFTMAX>();
+        const int t = warp >> 2;                 // query tile of this warpgroup
+        const int qt = qt0 + t;
+        const int r = threadIdx.x & 127;         // row within the tile = TMEM lane
+        const int q0 = qt * PF_BM;
         const int qrow = q0 + r;
         const bool row_valid = qrow < p.n_q;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t tS = trow + PF_TM_S + 128u * t, tO = trow + PF_TM_O + 128u * t;
         const float c = p.scale_log2;
         // rows past n_q read the last real mask row (their results are never stored): every lane of a warp takes the
         // same path, so the .sync.aligned tcgen05 instructions below always see a converged warp
         const char* mrow = (p.mask != nullptr && !p.causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
         const bool mask_vec = (((uintptr_t)p.mask | (uintptr_t)p.nb31) & 15) == 0;
         const int64_t vis = p.causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
-        const bool dumping = a.dump != nullptr && (int)blockIdx.x == a.dump_cta;
 
         float m_ref = -INFINITY, l = 0.f;
         int it = 0;
-        for (int j = pf_next_tile(p, a, qt, 0); j >= 0; j = pf_next_tile(p, a, qt, j + 1), it++) {
-            const int cls = pf_tile_class(p, a, qt, j);
-            const int b = it & 1;
-            mbar_wait(&sm.s_full[b], (it >> 1) & 1, a.dbg, 7);
-                __syncwarp();
+        // diagnostics (b200fa_debug_set): clock64 stamps of the first 64 iterations of row 0 of each tile of CTA dump_cta
+        long long* tl = (a.dump != nullptr && (int)blockIdx.x == a.dump_cta && r == 0) ? reinterpret_cast<long long*>(a.dump) + t * 64 * 8 : nullptr;
+        if (tl) tl[63 * 8 + 6] = clock64();
+        for (int j = j_lo; j < j_hi; j++) {
+            const int cls = (sm.cls2[j] >> (2 * t)) & 3;
+            if (cls == 2) continue;
+            if (tl && it < 64) tl[it * 8 + 0] = clock64();
+            mbar_wait(&sm.s_full[t], it & 1, a.dbg, 7);
+            if (tl && it < 64) tl[it * 8 + 1] = clock64();
+            __syncwarp();
             tc_fence_after();
+            if (p.dbg_mode == 2) {  // tuning aid (env B200FA_DBG_MODE=2): no softmax at all -> the loop runs at the pace of the tensor pipe
+                if (it > 0) { mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 10); __syncwarp(); }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.p_full[t]);
+                if (tl && it < 64) tl[it * 8 + 5] = clock64();
+                it++;
+                continue;
+            }
             uint32_t s[4][32];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) tmem_ld32(trow + PF_TM_S + 128u * b + 32u * q4, s[q4]);
+            for (int q4 = 0; q4 < 4; q4++) tmem_ld32(tS + 32u * q4, s[q4]);
             tmem_wait_ld();
-            if (dumping && it == 0) {
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++)
-#pragma unroll
-                    for (int i = 0; i < 32; i++) a.dump[r * 128 + q4 * 32 + i] = __uint_as_float(s[q4][i]);
-            }
+            if (tl && it < 64) tl[it * 8 + 2] = clock64();
             if (cls == 1) {
                 const int kv0 = j * PF_BN;
+                const int lim = (int)min((int64_t)(p.n_kv - 1), vis) - kv0;  // last visible column of this tile for this row
 #pragma unroll
                 for (int q4 = 0; q4 < 4; q4++) {
                     if (mrow != nullptr) {
@@ -219,10 +323,10 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                                 const uint4 mv = *reinterpret_cast<const uint4*>(mrow + (int64_t)(kv0 + q4 * 32 + v8 * 8) * 2);
                                 const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[u]));
-                                    s[q4][v8 * 8 + 2 * u] = __float_as_uint(__uint_as_float(s[q4][v8 * 8 + 2 * u]) + f.x * a.inv_scale);
-                                    s[q4][v8 * 8 + 2 * u + 1] = __float_as_uint(__uint_as_float(s[q4][v8 * 8 + 2 * u + 1]) + f.y * a.inv_scale);
+                                for (int e = 0; e < 4; e++) {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                                    s[q4][v8 * 8 + 2 * e] = __float_as_uint(__uint_as_float(s[q4][v8 * 8 + 2 * e]) + f.x * a.inv_scale);
+                                    s[q4][v8 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(s[q4][v8 * 8 + 2 * e + 1]) + f.y * a.inv_scale);
                                 }
                             }
                         } else {
@@ -234,13 +338,11 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const int kv = kv0 + q4 * 32 + i;
-                        if (kv >= p.n_kv || (int64_t)kv > vis) s[q4][i] = 0xff800000u;  // -inf
-                    }
+                    for (int i = 0; i < 32; i++)
+                        if (q4 * 32 + i > lim) s[q4][i] = 0xff800000u;  // -inf: past the sequence end or the causal limit
                 }
+                __syncwarp();
             }
-            __syncwarp();
             // ---- row max (raw scores; scale > 0 on this path) ----
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -249,13 +351,12 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                 for (int i = 0; i < 32; i++) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[q4][i]));
             const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
             const bool need = m_tile > m_ref + PF_RESCALE_THRESHOLD;  // also true for the first finite max
-            // Every waiter must observe EVERY phase of an mbarrier in order (a parity wait that skips a phase is satisfied by
-            // the phase before it), so pv_done(it-1) is waited for in every iteration: here when O has to be rescaled,
-            // otherwise just before this tile's P is published.
+            // pv_done(it-1) is observed in every iteration (phase rule): here when O has to be rescaled, otherwise just
+            // before this tile's P is published
             bool saw_pv = false;
             if (it > 0 && __any_sync(0xffffffffu, need)) {
                 // O currently holds sum_{tiles < it}; PV_{it-1} must have landed before we touch it
-                mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 8);
+                mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 8);
                 saw_pv = true;
                 __syncwarp();
                 tc_fence_after();
@@ -264,87 +365,145 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
 #pragma unroll
                 for (int q4 = 0; q4 < 4; q4++) {
                     uint32_t o[32];
-                    tmem_ld32(trow + PF_TM_O + 32u * q4, o);
+                    tmem_ld32(tO + 32u * q4, o);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st32(trow + PF_TM_O + 32u * q4, o);
+                    tmem_st32(tO + 32u * q4, o);
                 }
                 tmem_wait_st();
             }
             if (need) m_ref = m_tile;
             const float m_eff = (m_ref == -INFINITY) ? 0.f : m_ref;
+            if (tl && it < 64) tl[it * 8 + 3] = clock64();
             // ---- P = exp2(s*c - m), row sum, pack to f16, store over S ----
-            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+            // Written as explicit passes over 32-column blocks so that the 128 independent ex2 of a row are in flight
+            // ahead of their consumers (sum, pack); FFMA2 / FADD2 halve the fp32 issue slots.
+            const uint64_t cc = pack2(c, c), nm = pack2(-m_eff, -m_eff);
+            uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+            auto exp_block = [&](int q4) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t pk[32];
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const int q4 = h * 2 + (i >> 4), e = (i & 15) * 2;
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[q4][e]), c, -m_eff));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[q4][e + 1]), c, -m_eff));
-                    ls[i & 3] += p0 + p1;
-                    pk[i] = pack_half2(p0, p1);
+                for (int i = 0; i < 16; i++) {
+                    float x0, x1;
+                    unpack2(fma2(pack2(__uint_as_float(s[q4][2 * i]), __uint_as_float(s[q4][2 * i + 1])), cc, nm), x0, x1);
+                    s[q4][2 * i] = __float_as_uint(fast_exp2(x0));
+                    s[q4][2 * i + 1] = __float_as_uint(fast_exp2(x1));
                 }
-                tmem_st32(trow + PF_TM_S + 128u * b + 32u * h, pk);
+            };
+            auto sum_pack_block = [&](int q4, uint32_t (&pk)[32], int base) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float p0 = __uint_as_float(s[q4][2 * i]), p1 = __uint_as_float(s[q4][2 * i + 1]);
+                    ls2[i & 3] = add2(ls2[i & 3], pack2(p0, p1));
+                    pk[base + i] = pack_half2(p0, p1);
+                }
+            };
+            {
+                uint32_t pk[32];
+                exp_block(0); exp_block(1);
+                sum_pack_block(0, pk, 0);
+                exp_block(2);
+                sum_pack_block(1, pk, 16);
+                tmem_st32(tS, pk);
+                exp_block(3);
+                sum_pack_block(2, pk, 0);
+                sum_pack_block(3, pk, 16);
+                tmem_st32(tS + 32u, pk);
             }
-            l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            {
+                float a0, a1, b0, b1;
+                unpack2(add2(ls2[0], ls2[1]), a0, a1); unpack2(add2(ls2[2], ls2[3]), b0, b1);
+                l += (a0 + a1) + (b0 + b1);
+            }
+            if (tl && it < 64) tl[it * 8 + 4] = clock64();
             if (it > 0 && !saw_pv) {
-                mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 10);
+                mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 10);
                 __syncwarp();
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&sm.p_full[b]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.p_full[t]);
+            if (tl && it < 64) tl[it * 8 + 5] = clock64();
+            it++;
         }
 
         // ---- epilogue: O / l -> dst[(iq3*n_q + q)*n_head + head][D]   (flash-llama.h:434) ----
-        const int64_t orow = ((int64_t)iq3 * p.n_q + qrow) * p.n_head + iq2;
         if (it > 0) {
-            mbar_wait(&sm.pv_done, (it - 1) & 1, a.dbg, 9);
-                __syncwarp();
+            mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 9);
+            __syncwarp();
             tc_fence_after();
         }
         const float inv_l = l > 0.f ? 1.f / l : 0.f;
+        if (qt < a.n_q_tiles) {
+            // Each thread holds one whole output row; storing it directly would scatter 16-byte pieces over 32 lines per
+            // instruction.  Instead every warp transposes its 32 rows, 256 bytes of each at a time, through 8 KB of its
+            // tile's Q buffer — 16-byte chunk c of row i parked at chunk position c ^ (i & 15), conflict-free both ways —
+            // and writes two whole 256-byte row pieces per instruction.  Q_t is idle: pv_done[t](last) fired after every
+            // MMA this tile's issuer ever issued.  (K/V buffers may still be feeding the other tile.)
+            uint4* stg = reinterpret_cast<uint4*>(sm.q[t] + (warp & 3) * 8192);
+            const bool f32out = p.dst_type == B200FA_TYPE_F32;
+            const int row0 = q0 + (warp & 3) * 32;                 // first query row of this warp
+            const int64_t rstride = (int64_t)p.n_head * PF_D;      // elements between consecutive query rows of dst
+            const int64_t obase = (((int64_t)iq3 * p.n_q + row0) * p.n_head + iq2) * PF_D;
+            const int ri = lane >> 4, ch = lane & 15;               // store phase: lanes 0-15 one row, 16-31 the next
+            const int n_pass = f32out ? 2 : 1;                      // 64 f32 or 128 f16 columns = 256 bytes per pass
+            for (int pass = 0; pass < n_pass; pass++) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; q4++) {
-            uint32_t o[32];
-            if (it > 0) {
-                tmem_ld32(trow + PF_TM_O + 32u * q4, o);
-                tmem_wait_ld();
-            } else {
+                for (int h = 0; h < 2; h++) {
+                    const int q4 = f32out ? pass * 2 + h : h * 2;  // f16: blocks (0,1) then (2,3)
+                    uint32_t o[32], o2[32];
+                    if (it > 0) {
+                        tmem_ld32(tO + 32u * q4, o);
+                        if (!f32out) tmem_ld32(tO + 32u * (q4 + 1), o2);
+                        tmem_wait_ld();
+                    } else {
 #pragma unroll
-                for (int i = 0; i < 32; i++) o[i] = 0u;
-            }
-            if (dumping) {
+                        for (int i = 0; i < 32; i++) { o[i] = 0u; o2[i] = 0u; }
+                    }
+                    if (f32out) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) a.dump[128 * 128 + r * 128 + q4 * 32 + i] = __uint_as_float(o[i]);
-                if (q4 == 0) { a.dump[2 * 128 * 128 + r] = l; a.dump[2 * 128 * 128 + 128 + r] = m_ref; }
-            }
-            if (row_valid) {
-                if (p.dst_type == B200FA_TYPE_F32) {
-                    float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dst) + orow * PF_D + q4 * 32);
+                        for (int i = 0; i < 8; i++) {
+                            const int c16 = h * 8 + i;
+                            stg[lane * 16 + (c16 ^ (lane & 15))] =
+                                make_uint4(__float_as_uint(__uint_as_float(o[4 * i]) * inv_l), __float_as_uint(__uint_as_float(o[4 * i + 1]) * inv_l),
+                                           __float_as_uint(__uint_as_float(o[4 * i + 2]) * inv_l), __float_as_uint(__uint_as_float(o[4 * i + 3]) * inv_l));
+                        }
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        d4[i] = make_float4(__uint_as_float(o[4 * i]) * inv_l, __uint_as_float(o[4 * i + 1]) * inv_l,
-                                            __uint_as_float(o[4 * i + 2]) * inv_l, __uint_as_float(o[4 * i + 3]) * inv_l);
-                } else {
-                    uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.dst) + orow * PF_D + q4 * 32);
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        d4[i] = make_uint4(pack_half2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
-                                           pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
-                                           pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
-                                           pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t* src = i < 4 ? o : o2;
+                            const int b = (i & 3) * 8;
+                            const int c16 = h * 8 + i;
+                            stg[lane * 16 + (c16 ^ (lane & 15))] =
+                                make_uint4(pack_half2(__uint_as_float(src[b]) * inv_l, __uint_as_float(src[b + 1]) * inv_l),
+                                           pack_half2(__uint_as_float(src[b + 2]) * inv_l, __uint_as_float(src[b + 3]) * inv_l),
+                                           pack_half2(__uint_as_float(src[b + 4]) * inv_l, __uint_as_float(src[b + 5]) * inv_l),
+                                           pack_half2(__uint_as_float(src[b + 6]) * inv_l, __uint_as_float(src[b + 7]) * inv_l));
+                        }
+                    }
                 }
+                __syncwarp();
+                char* dbase = reinterpret_cast<char*>(p.dst) + (f32out ? (obase * 4 + pass * 256) : obase * 2);
+                const int64_t rbytes = rstride * (f32out ? 4 : 2);
+#pragma unroll 4
+                for (int i = 0; i < 32; i += 2) {
+                    const int rr = i + ri;
+                    if (row0 + rr < p.n_q) {
+                        const uint4 v = stg[rr * 16 + (ch ^ (rr & 15))];
+                        *reinterpret_cast<uint4*>(dbase + rr * rbytes + ch * 16) = v;
+                    }
+                }
+                __syncwarp();
             }
         }
     }
 
+    if (a.dump != nullptr && (int)blockIdx.x == a.dump_cta && (threadIdx.x & 127) == 0 && warp < 8)
+        reinterpret_cast<long long*>(a.dump)[(warp >> 2) * 64 * 8 + 63 * 8 + 7] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem, PF_TMEM_COLS);
     }
@@ -433,7 +592,7 @@ inline PfDebug& pf_debug() {
 inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes, size_t cls_bytes, int sm_count,
                                   cudaStream_t st, int* launches) {
     (void)sm_count; (void)cls_bytes;
-    if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f)) return B200FA_ERR_UNSUPPORTED;
+    if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PF_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
     int n = 0;
     const void* qbase = p.q;
     int64_t qnb1 = p.nb01, qnb2 = p.nb02, qnb3 = p.nb03;
@@ -449,6 +608,7 @@ inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes
     PfArgs a{};
     a.n_q_tiles = (p.n_q + PF_BM - 1) / PF_BM;
     a.n_kv_tiles = (p.n_kv + PF_BN - 1) / PF_BN;
+    a.n_q_pairs = (a.n_q_tiles + 1) / 2;
     a.inv_scale = 1.0f / p.scale;
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {
@@ -470,7 +630,7 @@ inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes
             return B200FA_ERR_CUDA;
         attr_set[dev] = true;
     }
-    const unsigned grid = (unsigned)((int64_t)a.n_q_tiles * p.n_head * p.n_batch);
+    const unsigned grid = (unsigned)((int64_t)a.n_q_pairs * p.n_head * p.n_batch);
     fa_prefill_tcgen05<<<grid, PF_THREADS, smem_bytes, st>>>(p, a, tq, tk, tv);
     n++;
     if (launches) *launches = n;
