@@ -25,6 +25,7 @@
 // Rule kept throughout: every waiter of an mbarrier observes every phase of it, in order.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -38,14 +39,15 @@ constexpr uint32_t PF_TMEM_COLS = 512;
 constexpr uint32_t PF_TM_S = 0, PF_TM_O = 256;     // tile t: S at PF_TM_S + 128*t, O at PF_TM_O + 128*t
 constexpr float PF_RESCALE_THRESHOLD = 8.0f;       // log2 units
 constexpr int PF_REGS_SOFTMAX = 216, PF_REGS_OTHER = 40;
-constexpr int PF_STAGGER_CYCLES = 1100;
+constexpr int PF_STAGGER_CYCLES = 500;
 constexpr int PF_MAX_KV_TILES = 4096;              // schedule capacity: n_kv <= 524288 on this path
 
 struct __align__(1024) PfShared {
     uint8_t q[2][PF_TILE_BYTES];  // per Q tile: [2 k-blocks][128 rows][64 d]  128B-swizzled, K-major
     uint8_t k[2][PF_TILE_BYTES];  // ring stage: same layout, rows = keys
     uint8_t v[2][PF_TILE_BYTES];  // ring stage: [2 d-halves][128 keys][64 d]  128B-swizzled, MN-major B operand
-    uint64_t q_full[2], k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done[2];
+    uint64_t q_full[2], k_full[2], k_empty[2], v_full[2], v_empty[2], pv_done[2];
+    uint64_t s_full[2][2], p_full[2][2];  // [query tile][half of the KV tile]
     uint32_t tmem_base;
     int j_lo, j_hi;               // KV tiles outside [j_lo, j_hi) are invisible to both query tiles
     uint8_t cls2[PF_MAX_KV_TILES];  // per KV tile: class for query tile 0 (bits 0-1) and 1 (bits 2-3)
@@ -112,9 +114,31 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     return r;
 }
 
+// 2^x for a pair, on the FMA/ALU pipes instead of the 16-per-clock MUFU: round-to-nearest split x = n + r with the
+// 1.5*2^23 magic add, degree-3 minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, below the
+// half-ulp of the f16 the result is rounded to), n added into the exponent field.  x is clamped at -125.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    const uint64_t x = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+    const uint64_t xf = add2(x, pack2(12582912.f, 12582912.f));
+    const uint64_t t = add2(xf, pack2(-12582912.f, -12582912.f));
+    const uint64_t r = fma2(t, pack2(-1.f, -1.f), x);
+    uint64_t q = fma2(pack2(0.0551716685f, 0.0551716685f), r, pack2(0.2426111251f, 0.2426111251f));
+    q = fma2(q, r, pack2(0.6932609677f, 0.6932609677f));
+    q = fma2(q, r, pack2(0.9999280572f, 0.9999280572f));
+    float q0, q1, f0, f1;
+    unpack2(q, q0, q1);
+    unpack2(xf, f0, f1);
+    e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(f0) << 23));
+    e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(f1) << 23));
+}
+
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// POLY: every POLY-th pair of exponentials of a row is evaluated by exp2_poly2 instead of MUFU.EX2 (0 = none)
+template <int POLY>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ PfArgs a,
                    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -137,7 +161,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
             mbar_init(&sm.q_full[s], 1);
             mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 2);  // one arrival per MMA issuer
             mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 2);
-            mbar_init(&sm.s_full[s], 1); mbar_init(&sm.p_full[s], 4);  // one arrival per softmax warp
+            for (int h = 0; h < 2; h++) { mbar_init(&sm.s_full[s][h], 1); mbar_init(&sm.p_full[s][h], 4); }  // p_full: one arrival per softmax warp
             mbar_init(&sm.pv_done[s], 1);
         }
         fence_barrier_init();
@@ -202,37 +226,44 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
             // elected thread running a lean loop:  PV_t(previous tile), QK_t(this tile), per KV tile of the schedule.
             const int t = warp - 9;
             if (elect_one()) {
-                constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, PF_BN, 0, 0);
                 constexpr uint32_t idesc_pv = make_idesc_f16(PF_BM, PF_D, 0, 1);
                 const uint64_t dq = make_smem_desc_sw128(smem_u32(sm.q[t]), 16, 1024);
                 const uint64_t dk[2] = {make_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), make_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024)};
                 const uint64_t dv[2] = {make_smem_desc_sw128(smem_u32(sm.v[0]), PF_TILE_BYTES / 2, 1024),
                                         make_smem_desc_sw128(smem_u32(sm.v[1]), PF_TILE_BYTES / 2, 1024)};
                 const uint32_t tS = tmem + PF_TM_S + 128u * t, tO = tmem + PF_TM_O + 128u * t;
-                int n_pv = 0;      // products issued so far = phase counter of p_full[t]
-                int pend = -1;     // stage whose V the pending P.V needs, or -1
+                // A KV tile is processed as two 64-key halves with their own score buffers S^0 / S^1 (64 TMEM columns each,
+                // P^h over the first 32 of them): while the softmax group works on one half the tensor pipe does P.V and the
+                // next Q.K^T of the other, so neither waits a full tile for the other.
+                constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, 64, 0, 0);
+                int n_tiles = 0;   // tiles of this query tile issued so far = phase counter of p_full[t][h]
+                int pend = -1;     // stage whose V the pending P.V products need, or -1
                 bool have_q = false;
-                auto flush_pv = [&]() {
-                    mbar_wait(&sm.p_full[t], n_pv & 1, a.dbg, 5);
+                auto issue_pv = [&](int h) {  // O_t += P^h V[64h .. 64h+63] of the pending tile
+                    mbar_wait(&sm.p_full[t][h], (n_tiles - 1) & 1, a.dbg, 5);
                     tc_fence_after();
-                    if (n_pv == 0) {
+                    if (n_tiles == 1 && h == 0) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, ks > 0);
+                        for (int ks = 0; ks < 4; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, ks > 0);
                     } else {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, 1u);
+                        for (int ks = 0; ks < 4; ks++) mma_ts(tO, tS + 64u * h + ks * 8, dv[pend] + (uint64_t)((h * 8192 + ks * 2048) >> 4), idesc_pv, 1u);
                     }
                     tc_commit(&sm.pv_done[t]);
-                    tc_commit(&sm.v_empty[pend]);
-                    n_pv++;
-                    pend = -1;
                 };
-                if (t == 1 && j_lo < j_hi && (sm.cls2[j_lo] & 3) != 2) {
-                    // Stagger the two tiles by about half a period so that one tile's softmax runs while the tensor pipe works
-                    // for the other from the first iteration on (left alone they only drift apart after ~6 iterations).
+                auto issue_qk = [&](int h, int st) {  // S^h = Q_t K[64h .. 64h+63]^T
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        const uint64_t off = (uint64_t)(((ks >> 2) * (PF_TILE_BYTES / 2) + (ks & 3) * 32) >> 4);
+                        mma_ss(tS + 64u * h, dq + off, dk[st] + off + (uint64_t)(h * 8192 >> 4), idesc_qk, ks > 0);
+                    }
+                    tc_commit(&sm.s_full[t][h]);
+                };
+                if (PF_STAGGER_CYCLES > 0 && t == 1 && j_lo < j_hi && (sm.cls2[j_lo] & 3) != 2) {
+                    // Start the second tile a little after the first so the two softmax groups do not begin in lock step.
                     // A one-shot wait on phase 0 of the other tile's barrier is safe: that phase cannot be followed by another
                     // complete one before this thread has looked (the next one needs a whole softmax first).
-                    mbar_wait(&sm.s_full[0], 0, a.dbg, 11);
+                    mbar_wait(&sm.s_full[0][0], 0, a.dbg, 11);
                     const long long t0 = clock64();
                     while (clock64() - t0 < PF_STAGGER_CYCLES) {}
                 }
@@ -243,18 +274,24 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                     const bool active = ((c2 >> (2 * t)) & 3) != 2;
                     const int st = u & 1;
                     const uint32_t ph = (u >> 1) & 1;
-                    if (pend >= 0) flush_pv();  // always before waiting on a later stage: the producer needs v_empty to move on
+                    // The pending P.V products are always issued before waiting on a later stage (the producer needs v_empty
+                    // to move on), interleaved with this tile's Q.K^T halves: PV^0 QK^0 PV^1 QK^1.
+                    if (pend >= 0) issue_pv(0);
                     mbar_wait(&sm.k_full[st], ph, a.dbg, 3);
                     if (active) {
                         if (!have_q) { mbar_wait(&sm.q_full[t], 0, a.dbg, 4); have_q = true; }
                         tc_fence_after();
-#pragma unroll
-                        for (int ks = 0; ks < 8; ks++) {
-                            const uint64_t off = (uint64_t)(((ks >> 2) * (PF_TILE_BYTES / 2) + (ks & 3) * 32) >> 4);
-                            mma_ss(tS, dq + off, dk[st] + off, idesc_qk, ks > 0);
-                        }
-                        tc_commit(&sm.s_full[t]);
+                        issue_qk(0, st);
+                    }
+                    if (pend >= 0) {
+                        issue_pv(1);
+                        tc_commit(&sm.v_empty[pend]);
+                        pend = -1;
+                    }
+                    if (active) {
+                        issue_qk(1, st);
                         tc_commit(&sm.k_empty[st]);
+                        n_tiles++;
                     } else {
                         mbar_arrive(&sm.k_empty[st]);
                     }
@@ -263,7 +300,11 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                     else mbar_arrive(&sm.v_empty[st]);
                     u++;
                 }
-                if (pend >= 0) flush_pv();
+                if (pend >= 0) {
+                    issue_pv(0);
+                    issue_pv(1);
+                    tc_commit(&sm.v_empty[pend]);
+                }
             }
         }
     } else {
@@ -285,156 +326,164 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
         const int64_t vis = p.causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
 
         float m_ref = -INFINITY, l = 0.f;
-        int it = 0;
-        // diagnostics (b200fa_debug_set): clock64 stamps of the first 64 iterations of row 0 of each tile of CTA dump_cta
+        int it = 0;   // tiles of this query tile done
+        int g = 0;    // half-tiles done = products the issuer has been handed = phase counter of pv_done[t]
+        // diagnostics (b200fa_debug_set): clock64 stamps of the first 64 half-iterations of row 0 of each tile of CTA dump_cta
         long long* tl = (a.dump != nullptr && (int)blockIdx.x == a.dump_cta && r == 0) ? reinterpret_cast<long long*>(a.dump) + t * 64 * 8 : nullptr;
         if (tl) tl[63 * 8 + 6] = clock64();
         for (int j = j_lo; j < j_hi; j++) {
             const int cls = (sm.cls2[j] >> (2 * t)) & 3;
             if (cls == 2) continue;
-            if (tl && it < 64) tl[it * 8 + 0] = clock64();
-            mbar_wait(&sm.s_full[t], it & 1, a.dbg, 7);
-            if (tl && it < 64) tl[it * 8 + 1] = clock64();
-            __syncwarp();
-            tc_fence_after();
-            if (p.dbg_mode == 2) {  // tuning aid (env B200FA_DBG_MODE=2): no softmax at all -> the loop runs at the pace of the tensor pipe
-                if (it > 0) { mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 10); __syncwarp(); }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.p_full[t]);
-                if (tl && it < 64) tl[it * 8 + 5] = clock64();
-                it++;
-                continue;
-            }
-            uint32_t s[4][32];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) tmem_ld32(tS + 32u * q4, s[q4]);
-            tmem_wait_ld();
-            if (tl && it < 64) tl[it * 8 + 2] = clock64();
-            if (cls == 1) {
-                const int kv0 = j * PF_BN;
-                const int lim = (int)min((int64_t)(p.n_kv - 1), vis) - kv0;  // last visible column of this tile for this row
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                    if (mrow != nullptr) {
-                        if (mask_vec && kv0 + PF_BN <= p.n_kv) {
-#pragma unroll
-                            for (int v8 = 0; v8 < 4; v8++) {
-                                const uint4 mv = *reinterpret_cast<const uint4*>(mrow + (int64_t)(kv0 + q4 * 32 + v8 * 8) * 2);
-                                const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                                    s[q4][v8 * 8 + 2 * e] = __float_as_uint(__uint_as_float(s[q4][v8 * 8 + 2 * e]) + f.x * a.inv_scale);
-                                    s[q4][v8 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(s[q4][v8 * 8 + 2 * e + 1]) + f.y * a.inv_scale);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; i++) {
-                                const int kv = kv0 + q4 * 32 + i;
-                                if (kv < p.n_kv) s[q4][i] = __float_as_uint(__uint_as_float(s[q4][i]) + ld_mask(mrow, kv) * a.inv_scale);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i++)
-                        if (q4 * 32 + i > lim) s[q4][i] = 0xff800000u;  // -inf: past the sequence end or the causal limit
-                }
-                __syncwarp();
-            }
-            // ---- row max (raw scores; scale > 0 on this path) ----
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-            for (int q4 = 0; q4 < 4; q4++)
-#pragma unroll
-                for (int i = 0; i < 32; i++) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[q4][i]));
-            const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
-            const bool need = m_tile > m_ref + PF_RESCALE_THRESHOLD;  // also true for the first finite max
-            // pv_done(it-1) is observed in every iteration (phase rule): here when O has to be rescaled, otherwise just
-            // before this tile's P is published
-            bool saw_pv = false;
-            if (it > 0 && __any_sync(0xffffffffu, need)) {
-                // O currently holds sum_{tiles < it}; PV_{it-1} must have landed before we touch it
-                mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 8);
-                saw_pv = true;
+#pragma unroll 1
+            for (int h = 0; h < 2; h++, g++) {
+                if (tl && g < 62) tl[g * 8 + 0] = clock64();
+                mbar_wait(&sm.s_full[t][h], it & 1, a.dbg, 7);
+                if (tl && g < 62) tl[g * 8 + 1] = clock64();
                 __syncwarp();
                 tc_fence_after();
-                const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.f;
-                l *= alpha;
+                const uint32_t tSh = tS + 64u * h;
+                if (p.dbg_mode == 2) {  // tuning aid (env B200FA_DBG_MODE=2): no softmax at all -> the loop runs at the pace of the tensor pipe
+                    if (g > 0) { mbar_wait(&sm.pv_done[t], (g - 1) & 1, a.dbg, 10); __syncwarp(); }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.p_full[t][h]);
+                    if (tl && g < 62) tl[g * 8 + 5] = clock64();
+                    continue;
+                }
+                uint32_t s[2][32];
+                tmem_ld32(tSh, s[0]);
+                tmem_ld32(tSh + 32u, s[1]);
+                tmem_wait_ld();
+                if (tl && g < 62) tl[g * 8 + 2] = clock64();
+                if (cls == 1) {
+                    const int kv0 = j * PF_BN + 64 * h;
+                    const int lim = (int)min((int64_t)(p.n_kv - 1), vis) - kv0;  // last visible column of this half for this row
 #pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                    uint32_t o[32];
-                    tmem_ld32(tO + 32u * q4, o);
-                    tmem_wait_ld();
+                    for (int q2 = 0; q2 < 2; q2++) {
+                        if (mrow != nullptr) {
+                            if (mask_vec && kv0 + 64 <= p.n_kv) {
 #pragma unroll
-                    for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st32(tO + 32u * q4, o);
+                                for (int v8 = 0; v8 < 4; v8++) {
+                                    const uint4 mv = *reinterpret_cast<const uint4*>(mrow + (int64_t)(kv0 + q2 * 32 + v8 * 8) * 2);
+                                    const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) {
+                                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                                        s[q2][v8 * 8 + 2 * e] = __float_as_uint(__uint_as_float(s[q2][v8 * 8 + 2 * e]) + f.x * a.inv_scale);
+                                        s[q2][v8 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(s[q2][v8 * 8 + 2 * e + 1]) + f.y * a.inv_scale);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; i++) {
+                                    const int kv = kv0 + q2 * 32 + i;
+                                    if (kv < p.n_kv) s[q2][i] = __float_as_uint(__uint_as_float(s[q2][i]) + ld_mask(mrow, kv) * a.inv_scale);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (q2 * 32 + i > lim) s[q2][i] = 0xff800000u;  // -inf: past the sequence end or the causal limit
+                    }
+                    __syncwarp();
+                }
+                // ---- row max (raw scores; scale > 0 on this path) ----
+                float mx[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) mx[e] = -INFINITY;
+#pragma unroll
+                for (int q2 = 0; q2 < 2; q2++)
+#pragma unroll
+                    for (int i = 0; i < 32; i++) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[q2][i]));
+                const float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
+                const bool need = m_tile > m_ref + PF_RESCALE_THRESHOLD;  // also true for the first finite max
+                // pv_done(g-1) is observed in every half-iteration (phase rule): here when O has to be rescaled, otherwise
+                // just before this half's P is published
+                bool saw_pv = false;
+                if (g > 0 && __any_sync(0xffffffffu, need)) {
+                    // O currently holds the sum over the halves before g; PV_{g-1} must have landed before we touch it
+                    mbar_wait(&sm.pv_done[t], (g - 1) & 1, a.dbg, 8);
+                    saw_pv = true;
+                    __syncwarp();
+                    tc_fence_after();
+                    const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.f;
+                    l *= alpha;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + 32u * q4, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + 32u * q4, o);
+                    }
+                    tmem_wait_st();
+                }
+                if (need) m_ref = m_tile;
+                const float m_eff = (m_ref == -INFINITY) ? 0.f : m_ref;
+                if (tl && g < 62) tl[g * 8 + 3] = clock64();
+                // ---- P = exp2(s*c - m), row sum, pack to f16, store over S^h ----
+                // Explicit passes over 32-column blocks keep the independent ex2 of a row in flight ahead of their consumers
+                // (sum, pack); FFMA2 / FADD2 halve the fp32 issue slots.
+                const uint64_t cc = pack2(c, c), nm = pack2(-m_eff, -m_eff);
+                uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+                auto exp_block = [&](int q2) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        float x0, x1;
+                        const uint64_t x2 = fma2(pack2(__uint_as_float(s[q2][2 * i]), __uint_as_float(s[q2][2 * i + 1])), cc, nm);
+                        if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 1) {
+                            exp2_poly2(x2, x0, x1);
+                        } else {
+                            unpack2(x2, x0, x1);
+                            x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+                        }
+                        s[q2][2 * i] = __float_as_uint(x0);
+                        s[q2][2 * i + 1] = __float_as_uint(x1);
+                    }
+                };
+                auto sum_pack_block = [&](int q2, uint32_t (&pk)[32], int base) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float p0 = __uint_as_float(s[q2][2 * i]), p1 = __uint_as_float(s[q2][2 * i + 1]);
+                        ls2[i & 3] = add2(ls2[i & 3], pack2(p0, p1));
+                        pk[base + i] = pack_half2(p0, p1);
+                    }
+                };
+                {
+                    uint32_t pk[32];
+                    exp_block(0); exp_block(1);
+                    sum_pack_block(0, pk, 0);
+                    sum_pack_block(1, pk, 16);
+                    tmem_st32(tSh, pk);
+                }
+                {
+                    float a0, a1, b0, b1;
+                    unpack2(add2(ls2[0], ls2[1]), a0, a1); unpack2(add2(ls2[2], ls2[3]), b0, b1);
+                    l += (a0 + a1) + (b0 + b1);
+                }
+                if (tl && g < 62) tl[g * 8 + 4] = clock64();
+                if (g > 0 && !saw_pv) {
+                    mbar_wait(&sm.pv_done[t], (g - 1) & 1, a.dbg, 10);
+                    __syncwarp();
                 }
                 tmem_wait_st();
-            }
-            if (need) m_ref = m_tile;
-            const float m_eff = (m_ref == -INFINITY) ? 0.f : m_ref;
-            if (tl && it < 64) tl[it * 8 + 3] = clock64();
-            // ---- P = exp2(s*c - m), row sum, pack to f16, store over S ----
-            // Written as explicit passes over 32-column blocks so that the 128 independent ex2 of a row are in flight
-            // ahead of their consumers (sum, pack); FFMA2 / FADD2 halve the fp32 issue slots.
-            const uint64_t cc = pack2(c, c), nm = pack2(-m_eff, -m_eff);
-            uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
-            auto exp_block = [&](int q4) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    float x0, x1;
-                    unpack2(fma2(pack2(__uint_as_float(s[q4][2 * i]), __uint_as_float(s[q4][2 * i + 1])), cc, nm), x0, x1);
-                    s[q4][2 * i] = __float_as_uint(fast_exp2(x0));
-                    s[q4][2 * i + 1] = __float_as_uint(fast_exp2(x1));
-                }
-            };
-            auto sum_pack_block = [&](int q4, uint32_t (&pk)[32], int base) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float p0 = __uint_as_float(s[q4][2 * i]), p1 = __uint_as_float(s[q4][2 * i + 1]);
-                    ls2[i & 3] = add2(ls2[i & 3], pack2(p0, p1));
-                    pk[base + i] = pack_half2(p0, p1);
-                }
-            };
-            {
-                uint32_t pk[32];
-                exp_block(0); exp_block(1);
-                sum_pack_block(0, pk, 0);
-                exp_block(2);
-                sum_pack_block(1, pk, 16);
-                tmem_st32(tS, pk);
-                exp_block(3);
-                sum_pack_block(2, pk, 0);
-                sum_pack_block(3, pk, 16);
-                tmem_st32(tS + 32u, pk);
-            }
-            {
-                float a0, a1, b0, b1;
-                unpack2(add2(ls2[0], ls2[1]), a0, a1); unpack2(add2(ls2[2], ls2[3]), b0, b1);
-                l += (a0 + a1) + (b0 + b1);
-            }
-            if (tl && it < 64) tl[it * 8 + 4] = clock64();
-            if (it > 0 && !saw_pv) {
-                mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 10);
+                tc_fence_before();
                 __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.p_full[t][h]);
+                if (tl && g < 62) tl[g * 8 + 5] = clock64();
             }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.p_full[t]);
-            if (tl && it < 64) tl[it * 8 + 5] = clock64();
             it++;
         }
 
         // ---- epilogue: O / l -> dst[(iq3*n_q + q)*n_head + head][D]   (flash-llama.h:434) ----
-        if (it > 0) {
-            mbar_wait(&sm.pv_done[t], (it - 1) & 1, a.dbg, 9);
+        if (g > 0) {
+            mbar_wait(&sm.pv_done[t], (g - 1) & 1, a.dbg, 9);
             __syncwarp();
             tc_fence_after();
         }
         const float inv_l = l > 0.f ? 1.f / l : 0.f;
+        if (tl) tl[63 * 8 + 0] = clock64();
         if (qt < a.n_q_tiles) {
             // Each thread holds one whole output row; storing it directly would scatter 16-byte pieces over 32 lines per
             // instruction.  Instead every warp transposes its 32 rows, 256 bytes of each at a time, through 8 KB of its
@@ -484,6 +533,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                     }
                 }
                 __syncwarp();
+                if (tl) tl[63 * 8 + 1 + 2 * pass] = clock64();
                 char* dbase = reinterpret_cast<char*>(p.dst) + (f32out ? (obase * 4 + pass * 256) : obase * 2);
                 const int64_t rbytes = rstride * (f32out ? 4 : 2);
 #pragma unroll 4
@@ -495,6 +545,7 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
                     }
                 }
                 __syncwarp();
+                if (tl) tl[63 * 8 + 2 + 2 * pass] = clock64();
             }
         }
     }
@@ -622,16 +673,18 @@ inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes
     if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13)) return B200FA_ERR_CUDA;
     if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23)) return B200FA_ERR_CUDA;
     constexpr size_t smem_bytes = sizeof(PfShared) + 1024;
-    static thread_local bool attr_set[64] = {};
+    static const int poly = getenv("B200FA_POLY") ? atoi(getenv("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
+    auto kern = poly == 2 ? fa_prefill_tcgen05<2> : (poly == 3 ? fa_prefill_tcgen05<3> : (poly == 4 ? fa_prefill_tcgen05<4> : fa_prefill_tcgen05<0>));
+    static thread_local bool attr_set[64][5] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(fa_prefill_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
+    if (dev >= 0 && dev < 64 && !attr_set[dev][poly & 3]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
             return B200FA_ERR_CUDA;
-        attr_set[dev] = true;
+        attr_set[dev][poly & 3] = true;
     }
     const unsigned grid = (unsigned)((int64_t)a.n_q_pairs * p.n_head * p.n_batch);
-    fa_prefill_tcgen05<<<grid, PF_THREADS, smem_bytes, st>>>(p, a, tq, tk, tv);
+    kern<<<grid, PF_THREADS, smem_bytes, st>>>(p, a, tq, tk, tv);
     n++;
     if (launches) *launches = n;
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;

@@ -31,6 +31,8 @@ for t in range(2):
     rows = st[t][st[t][:, 0] > 0]
     if len(rows) == 0: continue
     t0 = rows[0, 0]
+    e = st[t][63]
+    print(f"tile {t}: epilogue: last arrive -> pv_done seen {e[0] - rows[-1, 5]} | stage pass0 {e[1] - e[0]} | store pass0 {e[2] - e[1]} | stage pass1 {e[3] - e[2]} | store pass1 {e[4] - e[3]}")
     print(f"tile {t}: loop entered {st[t][63, 6] - t0} cycles before the first wait; epilogue finished {st[t][63, 7] - rows[-1, 5]} cycles after the last arrive")
     print(f"tile {t}: {len(rows)} iterations; per iteration: wait_S | tmem_ld | max(+resc) | exp+sum+pack | wait_pv+st+arrive | total   (cycles)")
     for i, r in enumerate(rows[:18]):
