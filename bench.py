@@ -336,8 +336,8 @@ def main():
 
     def run_c4():
         Hq, Hk, B, n_kv = 32, 8, 64, 8192
-        hk_local = Hk // world if Hk % world == 0 else Hk  # head-sharded: this rank owns Hk/world kv heads (+ their 4 q heads each)
-        hq_local = hk_local * (Hq // Hk)
+        hs = P.head_shard(Hq, Hk, rank, world)  # head-parallel: this rank owns a band of kv heads (+ their 4 q heads each)
+        hk_local, hq_local = hs.n_kv_heads, hs.n_q_heads
         k = rand_f16((B, hk_local, n_kv, D), 60); v = rand_f16((B, hk_local, n_kv, D), 61)
         q = torch.rand((B, hq_local, 1, D), device=dev) * 2 - 1
         mask = torch.zeros((32, n_kv), dtype=torch.float16, device=dev)
@@ -349,7 +349,7 @@ def main():
         nl = P.last_launch_count()
         _, t = time_steps(step, 40, 4, chunk=10)
         _, tk = time_steps(lambda i: step(i, P.FLAG_WORKSPACE_ZEROED), 40, 4, chunk=10)
-        total_bytes = 2 * B * Hk * n_kv * D * 2 if Hk % world == 0 else 2 * B * Hk * n_kv * D * 2 * world
+        total_bytes = 2 * B * Hk * n_kv * D * 2
         per_gpu = 2 * B * hk_local * n_kv * D * 2
         return {"config": f"c4: Llama-3-8B GQA decode 32q/8kv, batch 64, KV 8192 f16, head-sharded over {world} GPU(s) (strong scaling, no collective)",
                 "gbps_total": total_bytes / (t * 1e-3) / 1e9, "us_per_step": t * 1e3, "launches_per_step": nl,
@@ -358,7 +358,8 @@ def main():
 
     def run_c5():
         Hq, Hk, n_kv = 32, 8, 131072
-        n_local = n_kv // world
+        ss = P.seq_shard(n_kv, rank, world)
+        n_local = ss.n_local
         nsets = max(2, int(3 * L2_BYTES // (2 * Hk * n_local * 136)) + 1)
         ksets, vsets = [], []
         for s in range(nsets):
@@ -371,11 +372,11 @@ def main():
         dst = torch.empty((rows, D), dtype=torch.float32, device=dev)
         ws = P.Workspace(P.workspace_size(P.TYPE_F32, P.TYPE_Q8_0, D, 1, Hq, 1, n_local, Hk, 1))
         def local_step(i):
-            P.flash_attn_partial(q, ksets[i % nsets], vsets[i % nsets], kv_pos0=rank * n_local, n_kv_total=n_kv, workspace=ws, out=part)
+            P.flash_attn_partial(q, ksets[i % nsets], vsets[i % nsets], kv_pos0=ss.kv_pos0, n_kv_total=n_kv, workspace=ws, out=part)
         def full_step(i):
             local_step(i)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, part)
+                dist.all_gather_into_tensor(gathered.view(world * rows, D + 2), part)
                 P.merge_partials(gathered, dst=dst)
             else:
                 P.merge_partials(part.view(1, rows, D + 2), dst=dst)

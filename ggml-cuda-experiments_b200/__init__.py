@@ -11,3 +11,5 @@ from .api import (  # noqa: F401
     flash_attn_ext, flash_attn_ext_raw, flash_attn_partial, last_dispatch, last_launch_count, lib, merge_partials,
     quantize_q8_0, workspace_size)
 from .build import build  # noqa: F401
+from .sharding import (  # noqa: F401
+    HeadShard, SeqShard, flash_attn_ext_head_parallel, flash_attn_ext_seq_parallel, head_shard, seq_shard, slice_heads)
