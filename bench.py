@@ -155,6 +155,12 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # Libraries (NCCL's version banner, torch warnings) may write to stdout; the contract is ONE JSON line there.
+    # Everything but that line goes to stderr: fd 1 is pointed at fd 2 for the run and restored for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -456,7 +462,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "workloads": results,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
