@@ -9,6 +9,7 @@
 #include "decode_mma.cuh"
 #include "decode_stream.cuh"
 #include "prefill_tcgen05.cuh"
+#include "prefill_persistent.cuh"
 #include "q8_0.cuh"
 
 using namespace b200fa;
@@ -43,7 +44,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Workspace layout: [arrival counters: fixed kCtrRegion bytes at offset 0][everything else].  The counter region is
 // the same for every shape, so B200FA_FLAG_WORKSPACE_ZEROED stays valid when calls of different shapes share a workspace.
-constexpr size_t kCtrRegion = 65536 * sizeof(unsigned int);
+constexpr size_t kCtrRegion = 65536 * sizeof(unsigned int) + 256;  // + the persistent prefill kernel's two counters
+constexpr size_t kPrefillCtrOff = 65536 * sizeof(unsigned int);
 
 enum PlanKind { kPrefill, kStream, kRows16 };
 
@@ -362,7 +364,13 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (pl.kind == kPrefill) {
         g_last_dispatch = "prefill_tcgen05";
         int launches = 0;
-        rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
+        static const bool per_cta = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "cta");
+        if (per_cta || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
+            rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
+        } else {
+            if (!(flags & B200FA_FLAG_WORKSPACE_ZEROED) && cudaMemsetAsync(ws + kPrefillCtrOff, 0, 256, st) != cudaSuccess) return B200FA_ERR_CUDA;
+            rc = launch_prefill_persistent(p, ws + pl.ctr_bytes, pl.qf16_bytes, reinterpret_cast<unsigned int*>(ws + kPrefillCtrOff), di.sm_count, st, &launches);
+        }
         g_last_launches = launches;
         return rc;
     }

@@ -431,6 +431,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     if (stamp) a.timeline[blockIdx.x * 8 + 0] = dk_now();
 
     int i = 0, slot_idx = 0;
+    int n_def = 0, def_u[2] = {0, 0}, def_c0[2] = {0, 0}, def_n[2] = {0, 0};  // partial units of this CTA (at most the first and the last segment)
     while (i < my_chunks) {
         const long long x = start + i;
         const int u = (int)(x / a.cph), ch0 = (int)(x - (long long)u * a.cph);
@@ -546,66 +547,81 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
         }
         if (stamp) a.timeline[blockIdx.x * 8 + 3] = dk_now();
+        // Units shared with other CTAs are signalled and merged after the CTA's whole run (below): only its first and its
+        // last segment can be partial units, and a fence + atomic round trip in the middle of the stream would stall the
+        // consumers for longer than the ring can cover.
         if (n_contrib > 1) {
-            // ---- the last CTA of this unit to arrive merges the records (fa_reduce, flash_row_float.h:415-472:
-            //      M = max m_i, L = sum l_i 2^(m_i-M), O = sum O~_i 2^(m_i-M) / L — one parallel fp32 pass) ----
-            __threadfence();
-            bar_consumers();
-            if (threadIdx.x == 0) {
-                const unsigned int old = atomicInc(a.counters + u, (unsigned int)n_contrib - 1);  // wraps to 0: self-resetting
-                *s_flag = (old == (unsigned int)n_contrib - 1);
-            }
-            for (int cc = threadIdx.x; cc < n_contrib; cc += DK_CWARPS * 32) {  // record slot of contributor c0 + cc
-                const long long st = (c0 + cc) * a.total / G;
-                s_tab[cc] = (int)(c0 + cc) * a.max_slots + (u - (int)(st / a.cph));
-            }
-            bar_consumers();
-            if (*s_flag != 0) {
-                __threadfence();
-                for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
-                    const int R = idx / D, d = idx % D;
-                    // one pass, loads batched eight records at a time (they are independent: one L2 round trip per batch)
-                    float M = -INFINITY, L = 0.f, acc = 0.f;
-                    for (int cb = 0; cb < n_contrib; cb += 8) {
-                        float mm[8], ll[8], aa[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            const float* rec = a.rec + ((int64_t)s_tab[min(cb + e, n_contrib - 1)] * DK_REC_ROWS + R) * (D + DK_REC_PAD);
-                            mm[e] = __ldcg(rec + D); ll[e] = __ldcg(rec + D + 1); aa[e] = __ldcg(rec + d);
-                        }
-                        float Mb = M;
-#pragma unroll
-                        for (int e = 0; e < 8; e++) if (cb + e < n_contrib) Mb = fmaxf(Mb, mm[e]);
-                        const float Mu = (Mb == -INFINITY) ? 0.f : Mb;
-                        const float w0 = fast_exp2(M - Mu);  // M = -inf -> 0
-                        L *= w0; acc *= w0;
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            if (cb + e < n_contrib) {
-                                const float wt = fast_exp2(mm[e] - Mu);
-                                L += ll[e] * wt; acc += aa[e] * wt;
-                            }
-                        }
-                        M = Mb;
-                    }
-                    const int iq1 = R / p.gqa;
-                    const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
-                    if (p.dst != nullptr) {
-                        const float y = L > 0.f ? acc / L : 0.f;
-                        if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
-                        else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
-                    } else {
-                        float* out = p.part_out + orow * (D + 2);
-                        out[d] = acc;
-                        if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
-                    }
-                }
-            }
+            if (n_def < 2) { def_u[n_def] = u; def_c0[n_def] = (int)c0; def_n[n_def] = n_contrib; n_def++; }
         }
-        if (stamp) a.timeline[blockIdx.x * 8 + 4] = dk_now();
         slot_idx++;
         i = seg_end;
     }
+
+    // ---- partial units: publish the records, count arrivals; the last CTA of a unit to arrive merges its records
+    //      (fa_reduce, flash_row_float.h:415-472: M = max m_i, L = sum l_i 2^(m_i-M), O = sum O~_i 2^(m_i-M) / L —
+    //      here one parallel fp32 pass) ----
+    if (n_def == 0) {
+        if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; }
+        return;
+    }
+    __threadfence();
+    bar_consumers();
+    if (threadIdx.x < n_def) {
+        const unsigned int old = atomicInc(a.counters + def_u[threadIdx.x], (unsigned int)def_n[threadIdx.x] - 1);  // wraps to 0: self-resetting
+        s_flag[threadIdx.x] = (old == (unsigned int)def_n[threadIdx.x] - 1);
+    }
+    bar_consumers();
+    for (int k = 0; k < n_def; k++) {
+        if (s_flag[k] == 0) continue;
+        const int u = def_u[k], n_contrib = def_n[k];
+        const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
+        bar_consumers();  // s_tab is reused
+        for (int cc = threadIdx.x; cc < n_contrib; cc += DK_CWARPS * 32) {  // record slot of contributor c0 + cc
+            const long long st = (long long)(def_c0[k] + cc) * a.total / G;
+            s_tab[cc] = (def_c0[k] + cc) * a.max_slots + (u - (int)(st / a.cph));
+        }
+        bar_consumers();
+        __threadfence();
+        for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
+            const int R = idx / D, d = idx % D;
+            // one pass, loads batched eight records at a time (they are independent: one L2 round trip per batch)
+            float M = -INFINITY, L = 0.f, acc = 0.f;
+            for (int cb = 0; cb < n_contrib; cb += 8) {
+                float mm[8], ll[8], aa[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const float* rec = a.rec + ((int64_t)s_tab[min(cb + e, n_contrib - 1)] * DK_REC_ROWS + R) * (D + DK_REC_PAD);
+                    mm[e] = __ldcg(rec + D); ll[e] = __ldcg(rec + D + 1); aa[e] = __ldcg(rec + d);
+                }
+                float Mb = M;
+#pragma unroll
+                for (int e = 0; e < 8; e++) if (cb + e < n_contrib) Mb = fmaxf(Mb, mm[e]);
+                const float Mu = (Mb == -INFINITY) ? 0.f : Mb;
+                const float w0 = fast_exp2(M - Mu);  // M = -inf -> 0
+                L *= w0; acc *= w0;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (cb + e < n_contrib) {
+                        const float wt = fast_exp2(mm[e] - Mu);
+                        L += ll[e] * wt; acc += aa[e] * wt;
+                    }
+                }
+                M = Mb;
+            }
+            const int iq1 = R / p.gqa;
+            const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
+            if (p.dst != nullptr) {
+                const float y = L > 0.f ? acc / L : 0.f;
+                if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
+                else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+            } else {
+                float* out = p.part_out + orow * (D + 2);
+                out[d] = acc;
+                if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
+            }
+        }
+    }
+    if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; unsigned sm_id; asm("mov.u32 %0, %%smid;" : "=r"(sm_id)); a.timeline[blockIdx.x * 8 + 6] = sm_id; }
 }
 
 }  // namespace b200fa

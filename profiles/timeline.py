@@ -43,3 +43,13 @@ for it in range(3):
     for i, n in enumerate(names):
         col = s[:, i] - t0
         print(f"  {n:12s} min {col.min():7d}  med {int(np.median(col)):7d}  max {col.max():7d} ns")
+    if it == 2:
+        order = np.argsort(s[:, 2])
+        print("  per CTA (sorted by end of streaming): cta smid segs | first  stream_end  fold_done  end")
+        for o in list(order[:6]) + list(order[-24:]):
+            r = s[o]
+            print(f"    {o:4d} {r[6]:4d} {r[5]:2d} | {r[1]-t0:6d} {r[2]-t0:6d} {r[3]-t0:6d} {r[4]-t0:6d}")
+        for ns in (1, 2, 3):
+            sel = s[s[:, 5] == ns]
+            if len(sel):
+                print(f"  CTAs with {ns} segment(s): {len(sel)}; stream_end median {int(np.median(sel[:, 2] - t0))}, end median {int(np.median(sel[:, 4] - t0))}")
