@@ -268,8 +268,9 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
         if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.D)) return B200FA_ERR_CUDA;
         if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.D)) return B200FA_ERR_CUDA;
     }
-    const bool small = (int64_t)p.n_q * p.gqa <= 8;
     const bool q8 = p.kv_type == B200FA_TYPE_Q8_0;
+    static const int force_rh = getenv("B200FA_STREAM_RH") ? atoi(getenv("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
+    const bool small = (int64_t)p.n_q * p.gqa <= 8 && force_rh != 2;
     g_last_launches++;
 #define B200FA_STREAM(DD, KK) (small ? launch_stream_t<DD, KK, 1>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2>(p, a, pl.grid, tk, tv, st))
     if (p.D == 128) return q8 ? B200FA_STREAM(128, B200FA_TYPE_Q8_0) : B200FA_STREAM(128, B200FA_TYPE_F16);

@@ -96,7 +96,7 @@ __device__ __forceinline__ uint2 ld_q8x8(const char* p, bool al8) {
 }
 
 __device__ __forceinline__ uint16_t ld_u16(const char* p) { return __ldg(reinterpret_cast<const uint16_t*>(p)); }
-__device__ __forceinline__ float h_bits_to_f(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+__device__ __forceinline__ float h_bits_to_f(uint32_t b) { return __half2float(__ushort_as_half((unsigned short)b)); }
 
 // m16n8k16 with only rows 0-7 of A/C live (RH == 1): rows 8-15 are fed zeros and their outputs are dropped.
 __device__ __forceinline__ void mma_16816_top(float& c0, float& c1, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
@@ -113,8 +113,8 @@ struct KVTile {
     // f16: kf/vf hold ready fragments.  q8_0: raw int8 words (2 per 8 elements) + f16 scale bits.
     uint32_t kf[2][NC4][Q8 ? 2 : 4];
     uint32_t vf[4][NCV][Q8 ? 2 : 4];
-    uint16_t kd[Q8 ? 4 : 1][Q8 ? NC4 : 1];   // K block scales of this lane's 4 score columns
-    uint16_t vd[Q8 ? 4 : 1][Q8 ? NCV : 1];   // V block scale of (key 4t+i, the block holding dims 64c+8g..)
+    uint32_t kd[Q8 ? 4 : 1][Q8 ? NC4 : 1];   // K block scales (f16 bits) of this lane's 4 score columns
+    uint32_t vd[Q8 ? 4 : 1][Q8 ? NCV : 1];   // V block scale (f16 bits) of (key 4t+i, the block holding dims 64c+8g..)
     uint2 mk[2];                             // mask halves of keys kv0+4t..+3 for the lane's row(s)
 };
 
@@ -484,7 +484,7 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
                 } else {
                     q8x4_to_h2(T.vf[i][c][0], vv[i][0], vv[i][1]);
                     q8x4_to_h2(T.vf[i][c][1], vv[i][2], vv[i][3]);
-                    const __half2 d2 = __half2half2(__ushort_as_half(T.vd[i][c]));
+                    const __half2 d2 = __half2half2(__ushort_as_half((unsigned short)T.vd[i][c]));
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         __half2 x = __hmul2(*reinterpret_cast<__half2*>(&vv[i][u]), d2);  // RN(d*q) per element

@@ -376,7 +376,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int c = 0; c < NC4; c++) T.kd[i][c] = (uint16_t)lds_u16(sb + kdB + i * Geo::kRowBytes + c * kQ8BlockBytes);
+                for (int c = 0; c < NC4; c++) T.kd[i][c] = lds_u16(sb + kdB + i * Geo::kRowBytes + c * kQ8BlockBytes);
         }
         if (p.mask != nullptr) {
 #pragma unroll
@@ -406,9 +406,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                     const uint32_t b = sb + vB + i * Geo::kRowBytes + c * 2 * kQ8BlockBytes;
                     const uint32_t w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8);
                     T.vf[i][c][0] = __funnelshift_r(w0, w1, vsh); T.vf[i][c][1] = __funnelshift_r(w1, w2, vsh);
-                    // rows past the end of the sequence hold stale bytes: a zero scale keeps them out of P.V
-                    const uint32_t d = lds_u16(sb + vdB + i * Geo::kRowBytes + c * 2 * kQ8BlockBytes);
-                    T.vd[i][c] = (kv0 + 4 * t + i < p.n_kv) ? (uint16_t)d : (uint16_t)0;
+                    T.vd[i][c] = lds_u16(sb + vdB + i * Geo::kRowBytes + c * 2 * kQ8BlockBytes);
                 }
             }
         }
@@ -484,6 +482,15 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 read_k(T, sb, kv0, a.mask_bulk && key0 + DK_CHUNK <= p.n_kv);
                 qk_tile(T, s);
                 read_v(T, sb, kv0);
+                if constexpr (Q8) {
+                    if (key0 + DK_CHUNK > p.n_kv) {  // ragged last chunk: rows past the end hold stale bytes; a zero scale keeps them out of P.V
+#pragma unroll
+                        for (int i2 = 0; i2 < 4; i2++)
+#pragma unroll
+                            for (int c = 0; c < NCV; c++)
+                                if (kv0 + 4 * t + i2 >= p.n_kv) T.vd[i2][c] = 0u;
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);  // fragments are in registers: hand the stage back
