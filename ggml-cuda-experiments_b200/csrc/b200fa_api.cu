@@ -116,6 +116,12 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
         pl.n_units = (int)(n_head_kv * n_batch);
         pl.total_chunks = (long long)pl.n_units * pl.cph;
         int grid = sm_count;
+        // Few units: give every unit the same whole number of CTAs, so that no CTA's run crosses a unit boundary (a mid-run
+        // fold stalls the stream for longer than the ring covers) — as long as that leaves at most a fifth of the SMs idle.
+        if (pl.n_units <= sm_count) {
+            const int aligned = pl.n_units * (sm_count / pl.n_units);
+            if (aligned * 5 >= sm_count * 4) grid = aligned;
+        }
         if (const char* e = getenv("B200FA_STREAM_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
         if (grid > DK_TAB) grid = DK_TAB;
         pl.grid = (int)(pl.total_chunks < grid ? pl.total_chunks : grid);
