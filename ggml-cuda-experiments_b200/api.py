@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         l.b200fa_quantize_q8_0.argtypes = [vp, C.c_int, vp, i64, vp]
         l.b200fa_dequantize_q8_0.restype = C.c_int
         l.b200fa_dequantize_q8_0.argtypes = [vp, vp, i64, vp]
+        l.b200fa_kv_cache_append.restype = C.c_int
+        l.b200fa_kv_cache_append.argtypes = [vp, C.c_int, vp, C.c_int] + [i64] * 11 + [vp]
         l.b200fa_debug_timeline.restype = None
         l.b200fa_debug_timeline.argtypes = [vp]
         _lib = l
@@ -200,3 +202,21 @@ def dequantize_q8_0(y, stream=None):
     if rc != 0:
         raise B200FAError(rc, "b200fa_dequantize_q8_0")
     return out
+
+
+def kv_cache_append(src, cache, n_past: int, cache_type=None, stream=None):
+    """cache[b][head][n_past + i][:] = convert(src[b][i][head][:]).
+
+    src  : [n_batch][n_tokens][n_head_kv][D] f32 or f16 (any strides with contiguous rows) — the layout a projection produces
+    cache: [n_batch][n_head_kv][n_kv_max][D] f16 view, or uint8 [..][n_kv_max][D/32*34] for q8_0 (any strides)."""
+    st, ct = _type_of(src), _type_of(cache, cache_type)
+    n_b, n_tok, n_hk, D = src.shape
+    es = src.element_size()
+    ces = cache.element_size()
+    rc = lib().b200fa_kv_cache_append(
+        src.data_ptr(), st, cache.data_ptr(), ct, D, n_tok, n_hk, n_b,
+        src.stride(1) * es, src.stride(2) * es, src.stride(0) * es,
+        cache.stride(2) * ces, cache.stride(1) * ces, cache.stride(0) * ces, n_past, _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_kv_cache_append")
+    return cache

@@ -464,4 +464,25 @@ int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n, b200fa_stream
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
+int b200fa_kv_cache_append(const void* src, int src_type, void* cache, int cache_type, int64_t D, int64_t n_tokens, int64_t n_head_kv,
+                           int64_t n_batch, int64_t src_nb1, int64_t src_nb2, int64_t src_nb3, int64_t cache_nb1, int64_t cache_nb2,
+                           int64_t cache_nb3, int64_t n_past, b200fa_stream_t stream) {
+    if (!src || !cache || D <= 0 || D % 32 || n_tokens <= 0 || n_head_kv <= 0 || n_batch <= 0 || n_past < 0) return B200FA_ERR_INVALID;
+    if (src_type != B200FA_TYPE_F32 && src_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
+    if (cache_type != B200FA_TYPE_F16 && cache_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
+    const int64_t es = src_type == B200FA_TYPE_F32 ? 4 : 2;
+    if (((uintptr_t)src | src_nb1 | src_nb2 | src_nb3) % es || ((uintptr_t)cache | cache_nb1 | cache_nb2 | cache_nb3) % 2) return B200FA_ERR_INVALID;
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
+    const int64_t rows = n_tokens * n_head_kv * n_batch;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (src_type == B200FA_TYPE_F32)
+        kv_append_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const char*)src, (char*)cache, cache_type, (int)D, (int)n_tokens, (int)n_head_kv,
+                                                                      rows, src_nb1, src_nb2, src_nb3, cache_nb1, cache_nb2, cache_nb3, n_past);
+    else
+        kv_append_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const char*)src, (char*)cache, cache_type, (int)D, (int)n_tokens, (int)n_head_kv,
+                                                                       rows, src_nb1, src_nb2, src_nb3, cache_nb1, cache_nb2, cache_nb3, n_past);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
 }  // extern "C"

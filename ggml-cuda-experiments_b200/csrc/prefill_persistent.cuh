@@ -153,6 +153,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                 int u_tot = 0;       // K/V ring position
                 int tiles_tot = 0;   // tiles of this query tile issued so far (phase counter of p_full[t][h])
                 int nq = 0;          // Q_t tiles consumed so far (phase counter of q_full[t])
+                int n_work = 0;      // items in which this query tile had any work (phase counter of o_free[t])
                 for (int k = 0;; k++) {
                     const int slot = k & 1;
                     mbar_wait(&sm.item_full[slot], (k >> 1) & 1, a.dbg, 22);
@@ -166,10 +167,13 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                     for (int j = j_hi - 1; j >= j_lo; j--)
                         if (((sm.cls2[slot][j] >> (2 * t)) & 3) != 2) { j_last = j; break; }
                     int pend = -1;
-                    bool have_q = false, o_seen = (k == 0), first_pv = true;
+                    // o_free[t] is only used by items in which this query tile has work: those keep the softmax group and this
+                    // issuer in lock step through s_full / p_full.  (An idle softmax group could otherwise run two items — two
+                    // phases — ahead of its issuer, and a parity wait that is two phases late never returns.)
+                    bool have_q = false, o_seen = (n_work == 0), first_pv = true;
                     auto issue_pv = [&](int h) {  // O_t += P^h V[64h .. 64h+63] of the pending tile
                         mbar_wait(&sm.p_full[t][h], (tiles_tot - 1) & 1, a.dbg, 5);
-                        if (!o_seen) { mbar_wait(&sm.o_free[t], (k - 1) & 1, a.dbg, 23); o_seen = true; }  // previous item's O_t has been read out
+                        if (!o_seen) { mbar_wait(&sm.o_free[t], (n_work - 1) & 1, a.dbg, 23); o_seen = true; }  // the previous O_t has been read out
                         tc_fence_after();
                         if (first_pv) {
 #pragma unroll
@@ -232,7 +236,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                         }
                         nq++;
                     }
-                    if (!o_seen) mbar_wait(&sm.o_free[t], (k - 1) & 1, a.dbg, 23);  // keep the phase sequence whole
+                    if (j_last >= 0) n_work++;
                     mbar_arrive(&sm.item_empty[slot]);
                 }
             }
@@ -413,7 +417,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.o_free[t]);  // O_t is in registers: the next item may accumulate into it
+            if (g > 0 && lane == 0) mbar_arrive(&sm.o_free[t]);  // O_t is in registers: the next item may accumulate into it
             if (tl) tl[2] = clock64();
             const float inv_l = l > 0.f ? 1.f / l : 0.f;
             if (qt < a.n_q_tiles) {

@@ -34,4 +34,37 @@ __global__ void q8_0_dequantize_kernel(const uint8_t* __restrict__ x, float* __r
     y[b * 32 + lane] = __fmul_rn(d, (float)reinterpret_cast<const int8_t*>(blk + 2)[lane]);
 }
 
+// KV-cache append: rows of new K (or V) vectors -> the cache tensor at position n_past, converting on
+// the way: f32/f16 -> f16, or -> ggml q8_0 blocks (same rounding as q8_0_quantize_kernel).  This is the step the
+// reference's driver does by hand on the host (flash-matrix.cu:130-165).  One warp per (token, head, batch) row.
+template <typename T>
+__global__ void kv_append_kernel(const char* __restrict__ src, char* __restrict__ cache, int cache_type, int D, int n_tokens,
+                                 int n_head_kv, int64_t n_rows, int64_t snb1, int64_t snb2, int64_t snb3, int64_t cnb1, int64_t cnb2,
+                                 int64_t cnb3, int64_t n_past) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int tok = (int)(row % n_tokens), head = (int)((row / n_tokens) % n_head_kv);
+    const int64_t b = row / ((int64_t)n_tokens * n_head_kv);
+    const T* x = reinterpret_cast<const T*>(src + tok * snb1 + head * snb2 + b * snb3);
+    char* dst = cache + (n_past + tok) * cnb1 + head * cnb2 + b * cnb3;
+    for (int blk = 0; blk < D / 32; blk++) {
+        float v;
+        if constexpr (sizeof(T) == 2) v = __half2float(x[blk * 32 + lane]);
+        else v = x[blk * 32 + lane];
+        if (cache_type == B200FA_TYPE_F16) {
+            reinterpret_cast<__half*>(dst)[blk * 32 + lane] = __float2half_rn(v);
+        } else {
+            float amax = fabsf(v);
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+            const float d = __fdiv_rn(amax, 127.0f);
+            const float id = d ? __fdiv_rn(1.0f, d) : 0.0f;
+            uint8_t* qb = reinterpret_cast<uint8_t*>(dst) + blk * kQ8BlockBytes;
+            if (lane == 0) *reinterpret_cast<__half*>(qb) = __float2half_rn(d);
+            reinterpret_cast<int8_t*>(qb + 2)[lane] = (int8_t)roundf(__fmul_rn(v, id));
+        }
+    }
+}
+
 }  // namespace b200fa

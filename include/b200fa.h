@@ -138,6 +138,17 @@ int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, in
 int b200fa_quantize_q8_0(const void* src, int src_type, void* dst, int64_t n_elements, b200fa_stream_t stream);
 int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n_elements, b200fa_stream_t stream);
 
+/*
+ * KV-cache append: writes `n_tokens` new K (or V) rows per (kv head, batch) into the cache tensor at row `n_past`,
+ * converting f32/f16 -> f16 or -> q8_0 blocks on the way.  Replaces the host-side repacking loops of the reference's driver
+ * (flash-matrix.cu:130-165).  src element (d, tok, head, b) at src + tok*src_nb1 + head*src_nb2 + b*src_nb3 (+ d*elem);
+ * cache row (n_past + tok, head, b) at cache + (n_past+tok)*cache_nb1 + head*cache_nb2 + b*cache_nb3 — the same nb the
+ * attention entry takes for that tensor.  D % 32 == 0.
+ */
+int b200fa_kv_cache_append(const void* src, int src_type, void* cache, int cache_type, int64_t D, int64_t n_tokens,
+                           int64_t n_head_kv, int64_t n_batch, int64_t src_nb1, int64_t src_nb2, int64_t src_nb3,
+                           int64_t cache_nb1, int64_t cache_nb2, int64_t cache_nb3, int64_t n_past, b200fa_stream_t stream);
+
 /* Diagnostics: name of the kernel family the last b200fa_flash_attn_ext call on this thread dispatched to
  * ("decode_splitkv", "prefill_tcgen05", "rows16_mma"), and how many kernels it launched. */
 const char* b200fa_last_dispatch(void);

@@ -254,3 +254,35 @@ def test_stream_head_dim_64_q8_and_f16():
     Q, K, V = synth_qkv(64, 2, 776, 8, 2)  # 776 * 68 bytes per head: a multiple of 16, so q8_0 heads can be bulk-copied
     run_both(Q, K, V, None, q8=True)
     assert pkg().last_dispatch() == "decode_stream"
+
+
+# ---- KV-cache append (+ q8_0 quantise on the fly), then decode over the cache ----
+@pytest.mark.parametrize("q8", [False, True])
+def test_kv_cache_append_then_decode(q8):
+    import torch
+    P = pkg()
+    D, Hk, H, n_max, B = 128, 4, 16, 512, 2
+    n_past, n_new = 300, 5
+    Q, K, V = synth_qkv(D, 1, n_past + n_new, H, Hk, n_batch=B)
+    Kf, Vf = K.astype(np.float32), V.astype(np.float32)
+    if q8:
+        kc = torch.zeros((B, Hk, n_max, D // 32 * 34), dtype=torch.uint8, device="cuda"); vc = torch.zeros_like(kc)
+    else:
+        kc = torch.zeros((B, n_max, Hk, D), dtype=torch.float16, device="cuda").permute(0, 2, 1, 3); vc = torch.zeros_like(kc)  # cache view
+    # fill the past in one call, then append the new tokens (projection layout [b][tok][head][D], f32)
+    for cache, X in ((kc, Kf), (vc, Vf)):
+        P.kv_cache_append(to_dev(np.ascontiguousarray(X[:, :, :n_past].transpose(0, 2, 1, 3))), cache, 0, cache_type=P.TYPE_Q8_0 if q8 else None)
+        P.kv_cache_append(to_dev(np.ascontiguousarray(X[:, :, n_past:].transpose(0, 2, 1, 3))), cache, n_past, cache_type=P.TYPE_Q8_0 if q8 else None)
+    torch.cuda.synchronize()
+    n = n_past + n_new
+    if q8:  # byte-exact against the oracle's ggml quantiser
+        np.testing.assert_array_equal(kc[:, :, :n].cpu().numpy(), oracle.quantize_q8_0(Kf))
+        np.testing.assert_array_equal(vc[:, :, :n].cpu().numpy(), oracle.quantize_q8_0(Vf))
+        Kq, Vq = oracle.quantize_q8_0(Kf), oracle.quantize_q8_0(Vf)
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(Kq, 8), oracle.view_of(Vq, 8), None, 1 / np.sqrt(D), round_q_f16=True)
+    else:
+        np.testing.assert_array_equal(kc[:, :, :n].cpu().numpy(), K)
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), None, 1 / np.sqrt(D), round_q_f16=True)
+    out = P.flash_attn_ext(to_dev(Q), kc[:, :, :n], vc[:, :, :n], None, kv_type=P.TYPE_Q8_0 if q8 else None)
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy(), ref, "decode over the appended cache")

@@ -153,3 +153,62 @@ def test_vs_reference_cuda_flash_attn_ext_f16_prefill():
           f"ours-refgpu {np.abs(ours[0]-refgpu).max():.2e}")
     if np.all(np.abs(refgpu - ref32[0]) <= 2e-3 + 1e-2 * np.abs(ref32[0])):
         assert_close(ours[0], refgpu, "ours vs reference CUDA prefill", atol=4e-3, rtol=2e-2)
+
+
+# ---- persistent scheduler: more work items than SMs, uneven item costs, odd tile counts, batches ----
+@pytest.mark.parametrize("n_q,n_kv,H,Hk,B,causal", [(384, 384, 40, 8, 5, True),     # 2 pairs x 40 heads x 5 = 400 items > 148 SMs, odd tile count
+                                                      (640, 1152, 16, 16, 2, True),    # n_kv > n_q (chunked prefill), causal offset 512
+                                                      (130, 257, 12, 4, 13, False)])   # ragged everything, 156 items
+def test_persistent_many_items(n_q, n_kv, H, Hk, B, causal):
+    Q, K, V = synth_qkv(128, n_q, n_kv, H, Hk, n_batch=B)
+    if causal:
+        run_both(Q, K, V, make_mask("causal", n_q, n_kv), flags=pkg().FLAG_CAUSAL, drop_mask_for_product=True)
+    else:
+        run_both(Q, K, V, None)
+    _check_dispatch()
+
+
+def test_both_prefill_variants_agree(monkeypatch):
+    """The persistent kernel and the one-CTA-per-item kernel run the same pipeline: results agree to the last bit
+    of the f16 P rounding pattern (same tile order per row)."""
+    import subprocess, sys, json
+    code = r'''
+import sys, json
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import numpy as np, torch
+from common import synth_qkv
+from gpu_common import pkg, to_dev
+P = pkg()
+Q, K, V = synth_qkv(128, 512, 512, 6, 2)
+out = P.flash_attn_ext(to_dev(Q), to_dev(K), to_dev(V), None, flags=P.FLAG_CAUSAL)
+torch.cuda.synchronize()
+np.save(sys.argv[1], out.cpu().numpy())
+'''
+    import tempfile
+    outs = []
+    for variant in ("persistent", "cta"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ); env["B200FA_PREFILL"] = variant
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            outs.append(np.load(f.name))
+    assert np.abs(outs[0] - outs[1]).max() < 1e-6
+
+
+def test_full_size_properties_c3():
+    """BASELINE.json configs[2] at full size, size-independent properties: (i) linearity in V, (ii) a causal row is a
+    convex combination of the first i+1 value rows, (iii) rows of a non-causal call over a KV prefix equal the causal
+    rows that see exactly that prefix."""
+    import torch
+    P = pkg()
+    n, H = 2048, 32
+    Q, K, V = synth_qkv(128, n, n, H, H)
+    q, k, v = to_dev(Q.astype(np.float16)), to_dev(K), to_dev(V)
+    a = P.flash_attn_ext(q, k, v, None, flags=P.FLAG_CAUSAL).cpu().numpy()
+    b = P.flash_attn_ext(q, k, to_dev((2 * V.astype(np.float32)).astype(np.float16)), None, flags=P.FLAG_CAUSAL).cpu().numpy()
+    torch.cuda.synchronize()
+    assert np.abs(b - 2 * a).max() < 4e-3                                  # (i)
+    vmax = np.abs(V.astype(np.float32)).max()
+    assert np.abs(a).max() <= vmax + 1e-3                                   # (ii)
+    pre = 1024
+    c = P.flash_attn_ext(q[:, :, pre - 1:pre], k[:, :, :pre], v[:, :, :pre], None).cpu().numpy()   # decode-style call: row pre-1 over keys [0, pre)
+    assert np.abs(c[0, 0] - a[0, pre - 1]).max() < 2e-3                     # (iii)
