@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libb200fa.so")
 SOURCES = ["b200fa_api.cu"]
-HEADERS = ["common.cuh", "decode_mma.cuh", "prefill_tcgen05.cuh", "prefill_persistent.cuh", "decode_stream.cuh", "sm100_ptx.cuh", "q8_0.cuh", "../../include/b200fa.h"]
+HEADERS = ["common.cuh", "decode_mma.cuh", "prefill_tcgen05.cuh", "prefill_persistent.cuh", "prefill_persistent2.cuh", "decode_stream.cuh", "sm100_ptx.cuh", "q8_0.cuh", "../../include/b200fa.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -27,7 +27,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
+    extra = os.environ.get("B200FA_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
            *[os.path.join(CSRC, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -10,6 +10,7 @@
 #include "decode_stream.cuh"
 #include "prefill_tcgen05.cuh"
 #include "prefill_persistent.cuh"
+#include "prefill_persistent2.cuh"
 #include "q8_0.cuh"
 
 using namespace b200fa;

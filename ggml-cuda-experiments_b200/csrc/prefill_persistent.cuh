@@ -12,6 +12,8 @@
 //   o_free[t]                    softmax group t: O_t has been read out of TMEM -> the next item's first P.V may overwrite it
 // Every barrier keeps running phase counters across items, and every waiter still observes every phase in order.
 #pragma once
+#include <string.h>
+
 #include "prefill_tcgen05.cuh"
 
 namespace b200fa {
@@ -36,6 +38,185 @@ struct PpArgs {
     int n_items;               // n_q_pairs * n_head * n_batch
     unsigned int* counters;    // [0] next item to hand out (beyond the first gridDim.x), [1] CTAs finished; both zero between calls
 };
+
+// Role bodies shared by the persistent kernels (one or two softmax threads per query row).
+__device__ __forceinline__ void pp_decode_item(const FaParams& p, const PfArgs& a, int w, int& qt0, int& iq2, int& iq3) {
+    const int per_pair = p.n_head * p.n_batch;
+    qt0 = 2 * (a.n_q_pairs - 1 - w / per_pair);   // heavy (late) tile pairs first
+    const int rem = w % per_pair;
+    iq2 = rem % p.n_head; iq3 = rem / p.n_head;
+}
+
+__device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs& pa, PpShared& sm, int lane, const CUtensorMap& tmQ,
+                                                 const CUtensorMap& tmK, const CUtensorMap& tmV) {
+    using namespace ptx;
+    const PfArgs& a = pa.f;
+    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w, qt0, iq2, iq3); };
+    // ===================== producer warp: hands out items, builds their schedule, streams Q / K / V =====================
+    if (lane == 0) { prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); }
+    int u_tot = 0;           // K/V tiles streamed so far (ring position / phase)
+    int nq[2] = {0, 0};      // Q_t loads so far
+    for (int k = 0;; k++) {
+        const int slot = k & 1;
+        if (k >= 2) { mbar_wait(&sm.item_empty[slot], ((k >> 1) - 1) & 1, a.dbg, 20); __syncwarp(); }
+        int w = (int)blockIdx.x;
+        if (k > 0) {
+            if (lane == 0) w = (int)gridDim.x + (int)atomicAdd(pa.counters, 1u);
+            w = __shfl_sync(0xffffffffu, w, 0);
+        }
+        if (w >= pa.n_items) w = -1;
+        int qt0 = 0, iq2 = 0, iq3 = 0, lo = a.n_kv_tiles, hi = 0;
+        if (w >= 0) {
+            decode_item(w, qt0, iq2, iq3);
+            for (int j = lane; j < a.n_kv_tiles; j += 32) {
+                const int c = pf_tile_class(p, a, qt0, j) | (pf_tile_class(p, a, qt0 + 1, j) << 2);
+                sm.cls2[slot][j] = (uint8_t)c;
+                if (c != 0xA) { lo = min(lo, j); hi = max(hi, j + 1); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+        }
+        if (lane == 0) { sm.it_w[slot] = w; sm.it_jlo[slot] = lo; sm.it_jhi[slot] = hi; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.item_full[slot]);
+        if (w < 0) break;
+        if (lane == 0) {
+            const int ik2 = iq2 / p.gqa, ik3 = iq3 / p.rk3;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                if (qt0 + t >= a.n_q_tiles) continue;
+                if (nq[t] > 0) mbar_wait(&sm.q_empty[t], (nq[t] - 1) & 1, a.dbg, 21);
+                mbar_arrive_expect_tx(&sm.q_full[t], PF_TILE_BYTES);
+                tma_load_4d(sm.q[t], &tmQ, &sm.q_full[t], 0, (qt0 + t) * PF_BM, iq2, iq3);
+                tma_load_4d(sm.q[t] + PF_TILE_BYTES / 2, &tmQ, &sm.q_full[t], 64, (qt0 + t) * PF_BM, iq2, iq3);
+                nq[t]++;
+            }
+            for (int j = lo; j < hi; j++) {
+                if (sm.cls2[slot][j] == 0xA) continue;
+                const int st = u_tot & 1;
+                const uint32_t ph = (u_tot >> 1) & 1;
+                mbar_wait(&sm.k_empty[st], ph ^ 1, a.dbg, 1);
+                mbar_arrive_expect_tx(&sm.k_full[st], PF_TILE_BYTES);
+                tma_load_4d(sm.k[st], &tmK, &sm.k_full[st], 0, j * PF_BN, ik2, ik3);
+                tma_load_4d(sm.k[st] + PF_TILE_BYTES / 2, &tmK, &sm.k_full[st], 64, j * PF_BN, ik2, ik3);
+                mbar_wait(&sm.v_empty[st], ph ^ 1, a.dbg, 2);
+                mbar_arrive_expect_tx(&sm.v_full[st], PF_TILE_BYTES);
+                tma_load_4d(sm.v[st], &tmV, &sm.v_full[st], 0, j * PF_BN, ik2, ik3);
+                tma_load_4d(sm.v[st] + PF_TILE_BYTES / 2, &tmV, &sm.v_full[st], 64, j * PF_BN, ik2, ik3);
+                u_tot++;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& pa, PpShared& sm, uint32_t tmem, const int t) {
+    using namespace ptx;
+    const PfArgs& a = pa.f;
+    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w, qt0, iq2, iq3); };
+    // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 query tile 1 =====================
+    if (elect_one()) {
+        constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, 64, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_f16(PF_BM, PF_D, 0, 1);
+        const uint64_t dq = make_smem_desc_sw128(smem_u32(sm.q[t]), 16, 1024);
+        const uint64_t dk[2] = {make_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), make_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024)};
+        const uint64_t dv[2] = {make_smem_desc_sw128(smem_u32(sm.v[0]), PF_TILE_BYTES / 2, 1024),
+                                make_smem_desc_sw128(smem_u32(sm.v[1]), PF_TILE_BYTES / 2, 1024)};
+        const uint32_t tS = tmem + PF_TM_S + 128u * t, tO = tmem + PF_TM_O + 128u * t;
+        int u_tot = 0;       // K/V ring position
+        int tiles_tot = 0;   // tiles of this query tile issued so far (phase counter of p_full[t][h])
+        int nq = 0;          // Q_t tiles consumed so far (phase counter of q_full[t])
+        int n_work = 0;      // items in which this query tile had any work (phase counter of o_free[t])
+        for (int k = 0;; k++) {
+            const int slot = k & 1;
+            mbar_wait(&sm.item_full[slot], (k >> 1) & 1, a.dbg, 22);
+            const int w = sm.it_w[slot];
+            if (w < 0) break;
+            const int j_lo = sm.it_jlo[slot], j_hi = sm.it_jhi[slot];
+            int qt0, iq2, iq3;
+            decode_item(w, qt0, iq2, iq3);
+            const bool tile_valid = qt0 + t < a.n_q_tiles;
+            int j_last = -1;  // last KV tile this query tile needs: Q_t is released right after its Q.K^T
+            for (int j = j_hi - 1; j >= j_lo; j--)
+                if (((sm.cls2[slot][j] >> (2 * t)) & 3) != 2) { j_last = j; break; }
+            int pend = -1;
+            // o_free[t] is only used by items in which this query tile has work: those keep the softmax group and this
+            // issuer in lock step through s_full / p_full.  (An idle softmax group could otherwise run two items — two
+            // phases — ahead of its issuer, and a parity wait that is two phases late never returns.)
+            bool have_q = false, o_seen = (n_work == 0), first_pv = true;
+            auto issue_pv = [&](int h) {  // O_t += P^h V[64h .. 64h+63] of the pending tile
+                mbar_wait(&sm.p_full[t][h], (tiles_tot - 1) & 1, a.dbg, 5);
+                if (!o_seen) { mbar_wait(&sm.o_free[t], (n_work - 1) & 1, a.dbg, 23); o_seen = true; }  // the previous O_t has been read out
+                tc_fence_after();
+                if (first_pv) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, ks > 0);
+                    first_pv = false;
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) mma_ts(tO, tS + 64u * h + ks * 8, dv[pend] + (uint64_t)((h * 8192 + ks * 2048) >> 4), idesc_pv, 1u);
+                }
+                tc_commit(&sm.pv_done[t]);
+            };
+            auto issue_qk = [&](int h, int st) {  // S^h = Q_t K[64h .. 64h+63]^T
+#pragma unroll
+                for (int ks = 0; ks < 8; ks++) {
+                    const uint64_t off = (uint64_t)(((ks >> 2) * (PF_TILE_BYTES / 2) + (ks & 3) * 32) >> 4);
+                    mma_ss(tS + 64u * h, dq + off, dk[st] + off + (uint64_t)(h * 8192 >> 4), idesc_qk, ks > 0);
+                }
+                tc_commit(&sm.s_full[t][h]);
+            };
+            for (int j = j_lo; j < j_hi; j++) {
+                const int c2 = sm.cls2[slot][j];
+                if (c2 == 0xA) continue;
+                const bool active = ((c2 >> (2 * t)) & 3) != 2;
+                const int st = u_tot & 1;
+                const uint32_t ph = (u_tot >> 1) & 1;
+                if (pend >= 0) issue_pv(0);
+                mbar_wait(&sm.k_full[st], ph, a.dbg, 3);
+                if (active) {
+                    if (!have_q) { mbar_wait(&sm.q_full[t], nq & 1, a.dbg, 4); have_q = true; }
+                    tc_fence_after();
+                    issue_qk(0, st);
+                }
+                if (pend >= 0) {
+                    issue_pv(1);
+                    tc_commit(&sm.v_empty[pend]);
+                    pend = -1;
+                }
+                if (active) {
+                    issue_qk(1, st);
+                    tc_commit(&sm.k_empty[st]);
+                    if (j == j_last) tc_commit(&sm.q_empty[t]);
+                    tiles_tot++;
+                } else {
+                    mbar_arrive(&sm.k_empty[st]);
+                }
+                mbar_wait(&sm.v_full[st], ph, a.dbg, 6);
+                if (active) pend = st;
+                else mbar_arrive(&sm.v_empty[st]);
+                u_tot++;
+            }
+            if (pend >= 0) {
+                issue_pv(0);
+                issue_pv(1);
+                tc_commit(&sm.v_empty[pend]);
+            }
+            if (tile_valid) {
+                if (!have_q) {  // the tile was loaded but nothing of the KV range is visible to it: hand Q_t straight back
+                    mbar_wait(&sm.q_full[t], nq & 1, a.dbg, 4);
+                    mbar_arrive(&sm.q_empty[t]);
+                }
+                nq++;
+            }
+            if (j_last >= 0) n_work++;
+            mbar_arrive(&sm.item_empty[slot]);
+        }
+    }
+}
 
 template <int POLY>
 __global__ void __launch_bounds__(PF_THREADS, 1)
@@ -80,166 +261,9 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     if (warp >= 8) {
         reg_dec<PF_REGS_OTHER>();
         if (warp == 8) {
-            // ===================== producer warp: hands out items, builds their schedule, streams Q / K / V =====================
-            if (lane == 0) { prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); }
-            int u_tot = 0;           // K/V tiles streamed so far (ring position / phase)
-            int nq[2] = {0, 0};      // Q_t loads so far
-            for (int k = 0;; k++) {
-                const int slot = k & 1;
-                if (k >= 2) { mbar_wait(&sm.item_empty[slot], ((k >> 1) - 1) & 1, a.dbg, 20); __syncwarp(); }
-                int w = (int)blockIdx.x;
-                if (k > 0) {
-                    if (lane == 0) w = (int)gridDim.x + (int)atomicAdd(pa.counters, 1u);
-                    w = __shfl_sync(0xffffffffu, w, 0);
-                }
-                if (w >= pa.n_items) w = -1;
-                int qt0 = 0, iq2 = 0, iq3 = 0, lo = a.n_kv_tiles, hi = 0;
-                if (w >= 0) {
-                    decode_item(w, qt0, iq2, iq3);
-                    for (int j = lane; j < a.n_kv_tiles; j += 32) {
-                        const int c = pf_tile_class(p, a, qt0, j) | (pf_tile_class(p, a, qt0 + 1, j) << 2);
-                        sm.cls2[slot][j] = (uint8_t)c;
-                        if (c != 0xA) { lo = min(lo, j); hi = max(hi, j + 1); }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-                    }
-                }
-                if (lane == 0) { sm.it_w[slot] = w; sm.it_jlo[slot] = lo; sm.it_jhi[slot] = hi; }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.item_full[slot]);
-                if (w < 0) break;
-                if (lane == 0) {
-                    const int ik2 = iq2 / p.gqa, ik3 = iq3 / p.rk3;
-#pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        if (qt0 + t >= a.n_q_tiles) continue;
-                        if (nq[t] > 0) mbar_wait(&sm.q_empty[t], (nq[t] - 1) & 1, a.dbg, 21);
-                        mbar_arrive_expect_tx(&sm.q_full[t], PF_TILE_BYTES);
-                        tma_load_4d(sm.q[t], &tmQ, &sm.q_full[t], 0, (qt0 + t) * PF_BM, iq2, iq3);
-                        tma_load_4d(sm.q[t] + PF_TILE_BYTES / 2, &tmQ, &sm.q_full[t], 64, (qt0 + t) * PF_BM, iq2, iq3);
-                        nq[t]++;
-                    }
-                    for (int j = lo; j < hi; j++) {
-                        if (sm.cls2[slot][j] == 0xA) continue;
-                        const int st = u_tot & 1;
-                        const uint32_t ph = (u_tot >> 1) & 1;
-                        mbar_wait(&sm.k_empty[st], ph ^ 1, a.dbg, 1);
-                        mbar_arrive_expect_tx(&sm.k_full[st], PF_TILE_BYTES);
-                        tma_load_4d(sm.k[st], &tmK, &sm.k_full[st], 0, j * PF_BN, ik2, ik3);
-                        tma_load_4d(sm.k[st] + PF_TILE_BYTES / 2, &tmK, &sm.k_full[st], 64, j * PF_BN, ik2, ik3);
-                        mbar_wait(&sm.v_empty[st], ph ^ 1, a.dbg, 2);
-                        mbar_arrive_expect_tx(&sm.v_full[st], PF_TILE_BYTES);
-                        tma_load_4d(sm.v[st], &tmV, &sm.v_full[st], 0, j * PF_BN, ik2, ik3);
-                        tma_load_4d(sm.v[st] + PF_TILE_BYTES / 2, &tmV, &sm.v_full[st], 64, j * PF_BN, ik2, ik3);
-                        u_tot++;
-                    }
-                }
-                __syncwarp();
-            }
+            pp_producer_role(p, pa, sm, lane, tmQ, tmK, tmV);
         } else if (warp <= 10) {
-            // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 query tile 1 =====================
-            const int t = warp - 9;
-            if (elect_one()) {
-                constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, 64, 0, 0);
-                constexpr uint32_t idesc_pv = make_idesc_f16(PF_BM, PF_D, 0, 1);
-                const uint64_t dq = make_smem_desc_sw128(smem_u32(sm.q[t]), 16, 1024);
-                const uint64_t dk[2] = {make_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), make_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024)};
-                const uint64_t dv[2] = {make_smem_desc_sw128(smem_u32(sm.v[0]), PF_TILE_BYTES / 2, 1024),
-                                        make_smem_desc_sw128(smem_u32(sm.v[1]), PF_TILE_BYTES / 2, 1024)};
-                const uint32_t tS = tmem + PF_TM_S + 128u * t, tO = tmem + PF_TM_O + 128u * t;
-                int u_tot = 0;       // K/V ring position
-                int tiles_tot = 0;   // tiles of this query tile issued so far (phase counter of p_full[t][h])
-                int nq = 0;          // Q_t tiles consumed so far (phase counter of q_full[t])
-                int n_work = 0;      // items in which this query tile had any work (phase counter of o_free[t])
-                for (int k = 0;; k++) {
-                    const int slot = k & 1;
-                    mbar_wait(&sm.item_full[slot], (k >> 1) & 1, a.dbg, 22);
-                    const int w = sm.it_w[slot];
-                    if (w < 0) break;
-                    const int j_lo = sm.it_jlo[slot], j_hi = sm.it_jhi[slot];
-                    int qt0, iq2, iq3;
-                    decode_item(w, qt0, iq2, iq3);
-                    const bool tile_valid = qt0 + t < a.n_q_tiles;
-                    int j_last = -1;  // last KV tile this query tile needs: Q_t is released right after its Q.K^T
-                    for (int j = j_hi - 1; j >= j_lo; j--)
-                        if (((sm.cls2[slot][j] >> (2 * t)) & 3) != 2) { j_last = j; break; }
-                    int pend = -1;
-                    // o_free[t] is only used by items in which this query tile has work: those keep the softmax group and this
-                    // issuer in lock step through s_full / p_full.  (An idle softmax group could otherwise run two items — two
-                    // phases — ahead of its issuer, and a parity wait that is two phases late never returns.)
-                    bool have_q = false, o_seen = (n_work == 0), first_pv = true;
-                    auto issue_pv = [&](int h) {  // O_t += P^h V[64h .. 64h+63] of the pending tile
-                        mbar_wait(&sm.p_full[t][h], (tiles_tot - 1) & 1, a.dbg, 5);
-                        if (!o_seen) { mbar_wait(&sm.o_free[t], (n_work - 1) & 1, a.dbg, 23); o_seen = true; }  // the previous O_t has been read out
-                        tc_fence_after();
-                        if (first_pv) {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ks++) mma_ts(tO, tS + ks * 8, dv[pend] + (uint64_t)(ks * 2048 >> 4), idesc_pv, ks > 0);
-                            first_pv = false;
-                        } else {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ks++) mma_ts(tO, tS + 64u * h + ks * 8, dv[pend] + (uint64_t)((h * 8192 + ks * 2048) >> 4), idesc_pv, 1u);
-                        }
-                        tc_commit(&sm.pv_done[t]);
-                    };
-                    auto issue_qk = [&](int h, int st) {  // S^h = Q_t K[64h .. 64h+63]^T
-#pragma unroll
-                        for (int ks = 0; ks < 8; ks++) {
-                            const uint64_t off = (uint64_t)(((ks >> 2) * (PF_TILE_BYTES / 2) + (ks & 3) * 32) >> 4);
-                            mma_ss(tS + 64u * h, dq + off, dk[st] + off + (uint64_t)(h * 8192 >> 4), idesc_qk, ks > 0);
-                        }
-                        tc_commit(&sm.s_full[t][h]);
-                    };
-                    for (int j = j_lo; j < j_hi; j++) {
-                        const int c2 = sm.cls2[slot][j];
-                        if (c2 == 0xA) continue;
-                        const bool active = ((c2 >> (2 * t)) & 3) != 2;
-                        const int st = u_tot & 1;
-                        const uint32_t ph = (u_tot >> 1) & 1;
-                        if (pend >= 0) issue_pv(0);
-                        mbar_wait(&sm.k_full[st], ph, a.dbg, 3);
-                        if (active) {
-                            if (!have_q) { mbar_wait(&sm.q_full[t], nq & 1, a.dbg, 4); have_q = true; }
-                            tc_fence_after();
-                            issue_qk(0, st);
-                        }
-                        if (pend >= 0) {
-                            issue_pv(1);
-                            tc_commit(&sm.v_empty[pend]);
-                            pend = -1;
-                        }
-                        if (active) {
-                            issue_qk(1, st);
-                            tc_commit(&sm.k_empty[st]);
-                            if (j == j_last) tc_commit(&sm.q_empty[t]);
-                            tiles_tot++;
-                        } else {
-                            mbar_arrive(&sm.k_empty[st]);
-                        }
-                        mbar_wait(&sm.v_full[st], ph, a.dbg, 6);
-                        if (active) pend = st;
-                        else mbar_arrive(&sm.v_empty[st]);
-                        u_tot++;
-                    }
-                    if (pend >= 0) {
-                        issue_pv(0);
-                        issue_pv(1);
-                        tc_commit(&sm.v_empty[pend]);
-                    }
-                    if (tile_valid) {
-                        if (!have_q) {  // the tile was loaded but nothing of the KV range is visible to it: hand Q_t straight back
-                            mbar_wait(&sm.q_full[t], nq & 1, a.dbg, 4);
-                            mbar_arrive(&sm.q_empty[t]);
-                        }
-                        nq++;
-                    }
-                    if (j_last >= 0) n_work++;
-                    mbar_arrive(&sm.item_empty[slot]);
-                }
-            }
+            pp_issuer_role(p, pa, sm, tmem, warp - 9);
         }
     } else {
         // ===================== softmax / correction / epilogue: thread = query row =====================
@@ -483,74 +507,6 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             __threadfence();
         }
     }
-}
-
-inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_bytes, unsigned int* counters, int sm_count,
-                                     cudaStream_t st, int* launches) {
-    if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PP_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
-    int n = 0;
-    const void* qbase = p.q;
-    int64_t qnb1 = p.nb01, qnb2 = p.nb02, qnb3 = p.nb03;
-    if (p.q_type == B200FA_TYPE_F32) {
-        __half* q16 = reinterpret_cast<__half*>(ws);
-        const int64_t work = p.total_rows * (PF_D / 8);
-        fa_q_to_f16<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p.q, q16, PF_D, p.n_q, p.n_head, p.total_rows, p.nb01, p.nb02,
-                                                                   p.nb03);
-        n++;
-        qbase = q16;
-        qnb1 = PF_D * 2; qnb2 = (int64_t)p.n_q * PF_D * 2; qnb3 = (int64_t)p.n_head * p.n_q * PF_D * 2;
-    }
-    PpArgs pa{};
-    PfArgs& a = pa.f;
-    a.n_q_tiles = (p.n_q + PF_BM - 1) / PF_BM;
-    a.n_kv_tiles = (p.n_kv + PF_BN - 1) / PF_BN;
-    a.n_q_pairs = (a.n_q_tiles + 1) / 2;
-    a.inv_scale = 1.0f / p.scale;
-    a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
-    if (p.mask != nullptr && !p.causal) {
-        uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
-        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls);
-        n++;
-        a.cls = cls;
-    }
-    pa.n_items = a.n_q_pairs * p.n_head * p.n_batch;
-    pa.counters = counters;
-    CUtensorMap tq, tk, tv;
-    if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3)) return B200FA_ERR_CUDA;
-    if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13)) return B200FA_ERR_CUDA;
-    if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23)) return B200FA_ERR_CUDA;
-    CUtensorMap to;
-    {   // dst [batch][n_q][n_head][D]: box = 64 bytes x 1 head x 32 rows, 64-byte swizzle (the epilogue's staging layout)
-        PFN_encodeTiled enc = get_encode_tiled();
-        if (!enc) return B200FA_ERR_CUDA;
-        const bool f32o = p.dst_type == B200FA_TYPE_F32;
-        const cuuint64_t es = f32o ? 4 : 2;
-        cuuint64_t dims[4] = {(cuuint64_t)PF_D, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch};
-        cuuint64_t strides[3] = {(cuuint64_t)PF_D * es, (cuuint64_t)p.n_head * PF_D * es, (cuuint64_t)p.n_q * p.n_head * PF_D * es};
-        cuuint32_t box[4] = {(cuuint32_t)(64 / es), 1, 32, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&to, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.dst, dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return B200FA_ERR_CUDA;
-    }
-    constexpr size_t smem_bytes = sizeof(PpShared);
-    static_assert(smem_bytes <= 227 * 1024, "prefill shared memory budget");
-    static const int poly = getenv("B200FA_POLY") ? atoi(getenv("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
-    auto kern = poly == 0 ? fa_prefill_persistent<0> : fa_prefill_persistent<2>;
-    static thread_local bool attr_set[64][2] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev][poly == 0 ? 0 : 1]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
-            return B200FA_ERR_CUDA;
-        attr_set[dev][poly == 0 ? 0 : 1] = true;
-    }
-    const unsigned grid = (unsigned)(pa.n_items < sm_count ? pa.n_items : sm_count);
-    kern<<<grid, PF_THREADS, smem_bytes, st>>>(p, pa, tq, tk, tv, to);
-    n++;
-    if (launches) *launches = n;
-    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 }  // namespace b200fa
