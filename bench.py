@@ -299,7 +299,7 @@ def main():
     # ---------------------------------------------------------------- extra workloads (reported under "workloads")
     def run_c3():
         n, H = 2048, 32
-        nsets = 2
+        nsets = 4  # 4 x 48 MB of Q/K/V > 126 MB L2
         qs = [rand_f16((1, H, n, D), 30 + s) for s in range(nsets)]
         ks = [rand_f16((1, H, n, D), 40 + s) for s in range(nsets)]
         vs = [rand_f16((1, H, n, D), 50 + s) for s in range(nsets)]
@@ -313,7 +313,7 @@ def main():
                 P.flash_attn_ext(qs[i % nsets], ks[i % nsets], vs[i % nsets], m, dst=dst, flags=flags, workspace=ws)
             step(0); torch.cuda.synchronize()
             nl = P.last_launch_count(); disp = P.last_dispatch()
-            _, t = time_steps(step, 60, 5, chunk=20)
+            _, t = time_steps(step, 400, 10, chunk=50)
             tf = flops / (t * 1e-3) / 1e12
             out[name] = {"tflops": tf, "us_per_step": t * 1e3, "launches_per_step": nl, "dispatch": disp,
                          "frac_of_measured_bf16_peak": tf / peaks["bf16_tflops"], "frac_of_nominal_2250": tf / 2250.0}
