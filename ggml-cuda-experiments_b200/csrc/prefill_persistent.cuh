@@ -36,7 +36,9 @@ struct PpShared {
 struct PpArgs {
     PfArgs f;                  // classes, tile counts, inv_scale
     int n_items;               // n_q_pairs * n_head * n_batch
-    unsigned int* counters;    // [0] next item to hand out (beyond the first gridDim.x), [1] CTAs finished; both zero between calls
+    unsigned int* counters;    // [0] next item to hand out (beyond the first gridDim.x), [1] CTAs finished, [2] mask tiles that deviate
+                               // from the exactly-causal pattern (written by fa_mask_classify); all zero between calls
+    int detect_causal;         // a mask tensor was scanned: if counters[2] == 0 it is the causal mask and is synthesised instead of read
 };
 
 // Role bodies shared by the persistent kernels (one or two softmax threads per query row).
@@ -52,6 +54,7 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
     using namespace ptx;
     const PfArgs& a = pa.f;
     auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w, qt0, iq2, iq3); };
+    const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
     // ===================== producer warp: hands out items, builds their schedule, streams Q / K / V =====================
     if (lane == 0) { prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); }
     int u_tot = 0;           // K/V tiles streamed so far (ring position / phase)
@@ -69,7 +72,7 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
         if (w >= 0) {
             decode_item(w, qt0, iq2, iq3);
             for (int j = lane; j < a.n_kv_tiles; j += 32) {
-                const int c = pf_tile_class(p, a, qt0, j) | (pf_tile_class(p, a, qt0 + 1, j) << 2);
+                const int c = pf_tile_class(p, a, qt0, j, causal) | (pf_tile_class(p, a, qt0 + 1, j, causal) << 2);
                 sm.cls2[slot][j] = (uint8_t)c;
                 if (c != 0xA) { lo = min(lo, j); hi = max(hi, j + 1); }
             }
@@ -274,6 +277,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
         const uint32_t tS = trow + PF_TM_S + 128u * t, tO = trow + PF_TM_O + 128u * t;
         const float c = p.scale_log2;
         const bool mask_vec = (((uintptr_t)p.mask | (uintptr_t)p.nb31) & 15) == 0;
+        const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
         int it_tot = 0;   // tiles done over all items (phase counter of s_full[t][h])
         int g_tot = 0;    // half tiles done over all items (phase counter of pv_done[t])
         for (int k = 0;; k++) {
@@ -294,8 +298,8 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             const int qrow = q0 + r;
             // rows past n_q read the last real mask row (their results are never stored): every lane of a warp takes the
             // same path, so the .sync.aligned tcgen05 instructions below always see a converged warp
-            const char* mrow = (p.mask != nullptr && !p.causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
-            const int64_t vis = p.causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
+            const char* mrow = (p.mask != nullptr && !causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
+            const int64_t vis = causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
             float m_ref = -INFINITY, l = 0.f;
             int g = 0;  // half tiles of this item done
             for (int j = j_lo; j < j_hi; j++) {
@@ -504,6 +508,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
         if (atomicAdd(pa.counters + 1, 1u) == gridDim.x - 1) {
             pa.counters[0] = 0u;
             pa.counters[1] = 0u;
+            pa.counters[2] = 0u;
             __threadfence();
         }
     }

@@ -78,6 +78,7 @@ fa_prefill_persistent2(const __grid_constant__ FaParams p, const __grid_constant
         // It is idle whenever the staging buffer is in use (tile barriers separate the two uses).
         float* xchg = reinterpret_cast<float*>(sm.stage[t * 4 + qd][0]);
         uint4* stg = reinterpret_cast<uint4*>(sm.stage[t * 4 + qd][side]);  // this warp's 2 KB of epilogue staging
+        const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
         int it_tot = 0;   // tiles done over all items (phase counter of s_full[t][h])
         int g_tot = 0;    // half tiles done over all items (phase counter of pv_done[t])
         for (int k = 0;; k++) {
@@ -92,8 +93,8 @@ fa_prefill_persistent2(const __grid_constant__ FaParams p, const __grid_constant
             const int qt = qt0 + t;
             const int q0 = qt * PF_BM;
             const int qrow = q0 + r;
-            const char* mrow = (p.mask != nullptr && !p.causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
-            const int64_t vis = p.causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
+            const char* mrow = (p.mask != nullptr && !causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
+            const int64_t vis = causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
             float m_ref = -INFINITY, l = 0.f;   // l: this thread's half of the row sum
             int g = 0;
             bar_tile(t);  // both sides have left the previous item's epilogue: the exchange area is free again
@@ -290,6 +291,7 @@ fa_prefill_persistent2(const __grid_constant__ FaParams p, const __grid_constant
         if (atomicAdd(pa.counters + 1, 1u) == gridDim.x - 1) {
             pa.counters[0] = 0u;
             pa.counters[1] = 0u;
+            pa.counters[2] = 0u;
             __threadfence();
         }
     }
@@ -319,9 +321,10 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {
         uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
-        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls);
+        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2);
         n++;
         a.cls = cls;
+        pa.detect_causal = 1;
     }
     pa.n_items = a.n_q_pairs * p.n_head * p.n_batch;
     pa.counters = counters;

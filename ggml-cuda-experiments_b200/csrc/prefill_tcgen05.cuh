@@ -64,11 +64,13 @@ struct PfArgs {
 };
 
 // 0 = every element visible, 1 = mixed (mask / causal edge / ragged tail), 2 = nothing visible.  qt = 128-row tile index.
-__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j) {
+__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j, bool causal);
+__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j) { return pf_tile_class(p, a, qt, j, p.causal != 0); }
+__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j, bool causal) {
     const int kv0 = j * PF_BN;
     if (kv0 >= p.n_kv || qt >= a.n_q_tiles) return 2;
     int c = (kv0 + PF_BN > p.n_kv) ? 1 : 0;
-    if (p.causal) {
+    if (causal) {
         const int64_t q0 = (int64_t)qt * PF_BM;
         const int64_t first_lim = q0 + p.causal_off;
         const int64_t last_lim = min(q0 + PF_BM - 1, (int64_t)p.n_q - 1) + p.causal_off;
@@ -560,11 +562,32 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
     }
 }
 
-// One pass over the mask: class of every 128x128 tile (0 all zero, 2 all -inf, 1 anything else).
+// One pass over the mask: class of every 128x128 tile (0 all zero, 2 all -inf, 1 anything else).  Also counts, in
+// *not_causal (may be null), the tiles that deviate from the exactly-causal pattern "0 where kv <= q + (n_kv - n_q), -inf
+// elsewhere": a caller that passes the usual causal mask tensor without B200FA_FLAG_CAUSAL still gets the synthesised
+// mask (no per-element mask reads in the attention kernel).
 __global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__ mask, int64_t nb31, int n_q, int n_kv,
-                                                        int n_kv_tiles, uint8_t* __restrict__ cls) {
+                                                        int n_kv_tiles, uint8_t* __restrict__ cls, unsigned int* not_causal) {
     const int j = blockIdx.x, qt = blockIdx.y;
-    int has_zero = 0, has_ninf = 0, has_other = 0;
+    const int off = n_kv - n_q;
+    int has_zero = 0, has_ninf = 0, has_other = 0, deviates = 0;
+    const bool vec = ((((uintptr_t)mask | (uintptr_t)nb31) & 15) == 0) && (j + 1) * PF_BN <= n_kv;
+    if (vec) {  // aligned, whole tile: 16-byte loads, 8 mask values each
+        for (int idx = threadIdx.x; idx < PF_BM * (PF_BN / 8); idx += blockDim.x) {
+            const int r = qt * PF_BM + idx / (PF_BN / 8), col = j * PF_BN + (idx % (PF_BN / 8)) * 8;
+            if (r >= n_q) continue;
+            const uint4 v = *reinterpret_cast<const uint4*>(mask + (int64_t)r * nb31 + (int64_t)col * 2);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t bits = (w[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+                const bool visible = col + e <= r + off;
+                if ((bits & 0x7fffu) == 0) { has_zero = 1; if (!visible) deviates = 1; }
+                else if (bits == 0xfc00u) { has_ninf = 1; if (visible) deviates = 1; }
+                else { has_other = 1; deviates = 1; }
+            }
+        }
+    } else
     for (int idx = threadIdx.x; idx < PF_BM * (PF_BN / 2); idx += blockDim.x) {
         const int r = qt * PF_BM + idx / (PF_BN / 2), col = j * PF_BN + (idx % (PF_BN / 2)) * 2;
         if (r >= n_q) continue;
@@ -572,15 +595,20 @@ __global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__
         for (int e = 0; e < 2; e++) {
             if (col + e >= n_kv) continue;
             const uint16_t bits = *reinterpret_cast<const uint16_t*>(mask + (int64_t)r * nb31 + (int64_t)(col + e) * 2);
-            if ((bits & 0x7fffu) == 0) has_zero = 1;
-            else if (bits == 0xfc00u) has_ninf = 1;
-            else has_other = 1;
+            const bool visible = col + e <= r + off;
+            if ((bits & 0x7fffu) == 0) { has_zero = 1; if (!visible) deviates = 1; }
+            else if (bits == 0xfc00u) { has_ninf = 1; if (visible) deviates = 1; }
+            else { has_other = 1; deviates = 1; }
         }
     }
     has_zero = __syncthreads_or(has_zero);
     has_ninf = __syncthreads_or(has_ninf);
     has_other = __syncthreads_or(has_other);
-    if (threadIdx.x == 0) cls[(int64_t)qt * n_kv_tiles + j] = (has_other || (has_zero && has_ninf)) ? 1 : (has_ninf ? 2 : 0);
+    deviates = __syncthreads_or(deviates);
+    if (threadIdx.x == 0) {
+        cls[(int64_t)qt * n_kv_tiles + j] = (has_other || (has_zero && has_ninf)) ? 1 : (has_ninf ? 2 : 0);
+        if (deviates && not_causal != nullptr) atomicAdd(not_causal, 1u);
+    }
 }
 
 // f32 Q (any ggml strides) -> dense f16 [batch][head][q][D]; same rounding as the reference (flash-llama.h:80)
@@ -664,7 +692,7 @@ inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {
         uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
-        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls);
+        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, nullptr);
         n++;
         a.cls = cls;
     }
