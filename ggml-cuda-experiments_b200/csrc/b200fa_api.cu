@@ -57,7 +57,7 @@ struct Plan {
     int split_len = 0;
     int n_groups = 1;
     // stream-K decode
-    int cph = 0, n_units = 0, grid = 0, max_slots = 0, kv_end = 0;
+    int cph = 0, n_units = 0, grid = 0, max_slots = 0, kv_end = 0, cluster_k = 0;
     long long total_chunks = 0;
     size_t n_counters = 0;   // arrival counters needed (0 = none)
     size_t part_bytes = 0;   // split-KV partials / stream-K records
@@ -124,6 +124,12 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
             if (aligned * 5 >= sm_count * 4) grid = aligned;
         }
         if (const char* e = getenv("B200FA_STREAM_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
+        // unit-aligned grid with 2..8 CTAs per unit: launch each unit's CTAs as one thread-block cluster (DSMEM merge)
+        static const bool no_cluster = getenv("B200FA_NO_CLUSTER") != nullptr;
+        if (!no_cluster && pl.n_units > 0 && grid % pl.n_units == 0 && pl.total_chunks >= grid) {
+            const int k = grid / pl.n_units;
+            if (k >= 2 && k <= 8) pl.cluster_k = k;
+        }
         if (grid > DK_TAB) grid = DK_TAB;
         pl.grid = (int)(pl.total_chunks < grid ? pl.total_chunks : grid);
         const long long per = (pl.total_chunks + pl.grid - 1) / pl.grid;
@@ -259,6 +265,15 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev] = true;
     }
+    if (a.cluster_k > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = a.cluster_k; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    }
     fa_decode_stream<D, KV, RH><<<grid, DK_THREADS, smem, st>>>(p, a, tk, tv);
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
@@ -269,6 +284,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     a.counters = reinterpret_cast<unsigned int*>(ws);
     a.rec = reinterpret_cast<float*>(ws + pl.ctr_bytes);
     a.timeline = g_timeline;
+    a.cluster_k = pl.cluster_k;
     a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {

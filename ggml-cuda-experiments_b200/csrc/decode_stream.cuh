@@ -82,6 +82,8 @@ struct DkArgs {
     unsigned int* counters;  // [n_units], zero between calls
     int mask_bulk;           // mask rows can be staged with 128-byte bulk copies (16-byte aligned rows)
     unsigned long long* timeline;  // diagnostics: 8 globaltimer stamps per CTA, or null
+    int cluster_k;           // > 1: the grid is launched in clusters of cluster_k CTAs = the CTAs of one unit; their records are
+                             // merged through distributed shared memory (no global fence / atomic / L2 round trips)
 };
 __device__ __forceinline__ unsigned long long dk_now() {
     unsigned long long t;
@@ -111,6 +113,17 @@ __device__ __forceinline__ uint2 lds_u8x8(uint32_t a) {
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(DK_CWARPS * 32) : "memory"); }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local` (a shared-memory address of this CTA) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 // owner CTA of flat chunk x when CTA c covers [c*T/G, (c+1)*T/G)
 __device__ __forceinline__ long long dk_owner(long long x, long long T, long long G) { return ((x + 1) * G - 1) / T; }
 
@@ -128,6 +141,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     constexpr int NC4 = D / 32;  // 16-byte chunks per lane per K row == q8_0 blocks per row
     constexpr int NCV = D / 64;  // 64-wide halves of a V row
     constexpr int NT = D / 8;    // output n-tiles
+    constexpr int RLIVE = 8 * RH; // rows a CTA can hold
     using Tile = KVTile<D, Q8>;
 
     extern __shared__ uint8_t dk_smem_raw[];
@@ -194,6 +208,8 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 issue(i);
             }
         }
+        __syncwarp();
+        if (a.cluster_k > 1) cluster_sync_all();  // every thread of the cluster takes part in the cluster barrier
         return;
     }
     __syncthreads();
@@ -430,6 +446,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 
     int i = 0, slot_idx = 0;
     int n_def = 0, def_u[2] = {0, 0}, def_c0[2] = {0, 0}, def_n[2] = {0, 0};  // partial units of this CTA (at most the first and the last segment)
+    int cl_u = 0, cl_n = 1;  // cluster mode: the CTA's single unit and its contributor count
     while (i < my_chunks) {
         const long long x = start + i;
         const int u = (int)(x / a.cph), ch0 = (int)(x - (long long)u * a.cph);
@@ -538,7 +555,15 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 const int64_t orow = ((int64_t)iq3 * p.n_q + iq1r[RH == 1 ? 0 : h]) * p.n_head + ik2 * p.gqa + rq[RH == 1 ? 0 : h];  // flash-llama.h:434
                 const float M = Ms[RH == 1 ? 0 : h], L = Ls[RH == 1 ? 0 : h];
                 const bool first = (n == 0 && e1 == 0 && t == 0);  // one thread per row also stores (m, l)
-                if (n_contrib > 1) {
+                if (n_contrib > 1 && a.cluster_k > 1) {
+                    // record [rank][row][D + 2] in the leader CTA's (drained) stage ring; the cluster barrier below orders these
+                    // remote stores before the leader's loads.  The leader's own ring is idle: a cluster CTA has one segment,
+                    // and its last chunk was consumed before its fold began.
+                    const uint32_t rank = blockIdx.x % a.cluster_k;
+                    const uint32_t base = cluster_map(stages_u32, 0) + ((rank * RLIVE + R) * (D + 2)) * 4;
+                    st_cluster_f32(base + d * 4, acc);
+                    if (first) { st_cluster_f32(base + D * 4, M); st_cluster_f32(base + (D + 1) * 4, L); }
+                } else if (n_contrib > 1) {
                     float* rec = a.rec + (((int64_t)blockIdx.x * a.max_slots + slot_idx) * DK_REC_ROWS + R) * (D + DK_REC_PAD);
                     rec[d] = acc;
                     if (first) { rec[D] = M; rec[D + 1] = L; }  // log2 units inside the kernel
@@ -557,11 +582,46 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         // Units shared with other CTAs are signalled and merged after the CTA's whole run (below): only its first and its
         // last segment can be partial units, and a fence + atomic round trip in the middle of the stream would stall the
         // consumers for longer than the ring can cover.
-        if (n_contrib > 1) {
+        if (n_contrib > 1 && a.cluster_k <= 1) {
             if (n_def < 2) { def_u[n_def] = u; def_c0[n_def] = (int)c0; def_n[n_def] = n_contrib; n_def++; }
         }
+        if (a.cluster_k > 1) { cl_u = u; cl_n = n_contrib; }
         slot_idx++;
         i = seg_end;
+    }
+
+    if (a.cluster_k > 1) {
+        // ---- cluster mode: the unit's CTAs are one thread-block cluster; their records sit in the leader's shared memory ----
+        cluster_sync_all();
+        if (blockIdx.x % a.cluster_k != 0 || cl_n <= 1) return;
+        const int u = cl_u, n_contrib = cl_n;
+        const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
+        const float* recs = reinterpret_cast<const float*>(smem);
+        for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
+            const int R = idx / D, d = idx % D;
+            float M = -INFINITY;
+            for (int cc = 0; cc < n_contrib; cc++) M = fmaxf(M, recs[(cc * RLIVE + R) * (D + 2) + D]);
+            const float Mu = (M == -INFINITY) ? 0.f : M;
+            float L = 0.f, acc = 0.f;
+            for (int cc = 0; cc < n_contrib; cc++) {
+                const float* rec = recs + (cc * RLIVE + R) * (D + 2);
+                const float wt = fast_exp2(rec[D] - Mu);
+                L += rec[D + 1] * wt; acc += rec[d] * wt;
+            }
+            const int iq1 = R / p.gqa;
+            const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
+            if (p.dst != nullptr) {
+                const float y = L > 0.f ? acc / L : 0.f;
+                if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
+                else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+            } else {
+                float* out = p.part_out + orow * (D + 2);
+                out[d] = acc;
+                if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
+            }
+        }
+        if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; }
+        return;
     }
 
     // ---- partial units: publish the records, count arrivals; the last CTA of a unit to arrive merges its records
