@@ -400,10 +400,28 @@ def main():
             full_step(i)
         e1.record(); torch.cuda.synchronize(); barrier()
         t_full = max_over_ranks(e0.elapsed_time(e1) / 60)
+        # the same step with the combine over peer-mapped memory (NVLink stores + device-side wait) instead of NCCL
+        t_peer = None; t_fused = None
+        if world > 1:
+            try:
+                xch = P.PeerExchange.distributed(rows, D)
+                barrier()
+                def peer_step(i):
+                    P.flash_attn_partial_scatter(q, ksets[i % nsets], vsets[i % nsets], xch, kv_pos0=ss.kv_pos0, n_kv_total=n_kv, workspace=ws, flags=P.FLAG_WORKSPACE_ZEROED)
+                    P.merge_partials_wait(xch, dst=dst)
+                _, t_peer = time_steps(peer_step, 120, 5, chunk=20)  # the step number lives on the device: graph-replayable
+                def fused_step(i):
+                    P.flash_attn_seqpar(q, ksets[i % nsets], vsets[i % nsets], xch, kv_pos0=ss.kv_pos0, n_kv_total=n_kv, workspace=ws, dst=dst, flags=P.FLAG_WORKSPACE_ZEROED)
+                _, t_fused = time_steps(fused_step, 120, 5, chunk=20)
+                xch.close()
+            except Exception as e:  # noqa: BLE001
+                t_peer = repr(e)
         return {"config": f"c5: Llama-3-8B decode, KV 131072 q8_0 (34 B / 32 elems), sequence-split over {world} GPU(s), "
                           f"{'NCCL all-gather of (m,l,O) + merge' if world > 1 else 'single-GPU merge'}",
                 "stream_gbps_per_gpu": per_gpu / (t_local * 1e-3) / 1e9, "stream_frac_of_measured_hbm": per_gpu / (t_local * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "stream_us": t_local * 1e3, "end_to_end_us_stream_launch": t_full * 1e3, "gbps_total_end_to_end": world * per_gpu / (t_full * 1e-3) / 1e9,
+                "end_to_end_us_peer_memory_combine": (t_peer * 1e3 if isinstance(t_peer, float) else t_peer),
+                "end_to_end_us_fused_one_kernel": (t_fused * 1e3 if isinstance(t_fused, float) else t_fused),
                 "kv_bytes_per_gpu": per_gpu, "combine_payload_bytes_per_rank": rows * (D + 2) * 4, "launches_local": nl,
                 "l2": f"{nsets} rotating q8_0 K/V sets of {per_gpu / 1e6:.0f} MB per GPU"}
 

@@ -50,6 +50,22 @@ def lib() -> C.CDLL:
         l.b200fa_quantize_q8_0.argtypes = [vp, C.c_int, vp, i64, vp]
         l.b200fa_dequantize_q8_0.restype = C.c_int
         l.b200fa_dequantize_q8_0.argtypes = [vp, vp, i64, vp]
+        l.b200fa_xchg_bytes.restype = C.c_size_t
+        l.b200fa_xchg_bytes.argtypes = [C.c_int, i64, i64]
+        l.b200fa_flash_attn_partial_scatter.restype = C.c_int
+        l.b200fa_flash_attn_partial_scatter.argtypes = [vp] * 4 + [C.c_float] + [C.c_int] * 2 + [i64] * 21 + [vp, vp, C.c_int, C.c_int, C.c_uint32, vp, C.c_size_t, vp]
+        l.b200fa_flash_attn_seqpar.restype = C.c_int
+        l.b200fa_flash_attn_seqpar.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 3 + [i64] * 21 + [vp, vp, C.c_int, C.c_int, C.c_uint32, vp, C.c_size_t, vp]
+        l.b200fa_merge_partials_wait.restype = C.c_int
+        l.b200fa_merge_partials_wait.argtypes = [vp, C.c_int, i64, i64, vp, C.c_int, vp]
+        l.b200fa_peer_alloc.restype = C.c_int
+        l.b200fa_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+        l.b200fa_peer_open.restype = C.c_int
+        l.b200fa_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        l.b200fa_peer_close.restype = C.c_int
+        l.b200fa_peer_close.argtypes = [vp]
+        l.b200fa_peer_free.restype = C.c_int
+        l.b200fa_peer_free.argtypes = [vp]
         l.b200fa_kv_cache_append.restype = C.c_int
         l.b200fa_kv_cache_append.argtypes = [vp, C.c_int, vp, C.c_int] + [i64] * 11 + [vp]
         l.b200fa_debug_timeline.restype = None
@@ -220,3 +236,118 @@ def kv_cache_append(src, cache, n_past: int, cache_type=None, stream=None):
     if rc != 0:
         raise B200FAError(rc, "b200fa_kv_cache_append")
     return cache
+
+
+class PeerExchange:
+    """Exchange buffers for the sequence-split combine over peer-mapped memory (b200fa_flash_attn_partial_scatter /
+    b200fa_merge_partials_wait).  `PeerExchange.local(world, rows, D)` emulates `world` ranks on ONE device (tests);
+    `PeerExchange.distributed(rows, D, group)` allocates this rank's buffer, exchanges cudaIpc handles through
+    torch.distributed and maps every peer's buffer (one process per GPU on one node)."""
+
+    def __init__(self, world, rank, rows, D, own_ptr, peer_ptrs, owned, opened):
+        import torch
+        self.world, self.rank, self.rows, self.D = world, rank, rows, D
+        self.own_ptr, self.peer_ptrs, self._owned, self._opened = own_ptr, list(peer_ptrs), owned, opened
+        self.peers_dev = torch.tensor(self.peer_ptrs, dtype=torch.int64, device="cuda")  # device array of pointers
+
+    @staticmethod
+    def nbytes(world, rows, D):
+        return lib().b200fa_xchg_bytes(world, rows, D)
+
+    @classmethod
+    def local(cls, world, rows, D):
+        """`world` buffers on the current device; returns one PeerExchange per emulated rank."""
+        ptrs, handles = [], []
+        for _ in range(world):
+            p = C.c_void_p(); h = C.create_string_buffer(64)
+            rc = lib().b200fa_peer_alloc(cls.nbytes(world, rows, D), C.byref(p), h)
+            if rc != 0:
+                raise B200FAError(rc, "b200fa_peer_alloc")
+            ptrs.append(p.value)
+        return [cls(world, r, rows, D, ptrs[r], ptrs, owned=[ptrs[r]], opened=[]) for r in range(world)]
+
+    @classmethod
+    def distributed(cls, rows, D, group=None):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        p = C.c_void_p(); h = C.create_string_buffer(64)
+        rc = lib().b200fa_peer_alloc(cls.nbytes(world, rows, D), C.byref(p), h)
+        if rc != 0:
+            raise B200FAError(rc, "b200fa_peer_alloc")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        ptrs, opened = [], []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(p.value)
+            else:
+                q = C.c_void_p()
+                rc = lib().b200fa_peer_open(handles[r], C.byref(q))
+                if rc != 0:
+                    raise B200FAError(rc, "b200fa_peer_open")
+                ptrs.append(q.value); opened.append(q.value)
+        return cls(world, rank, rows, D, p.value, ptrs, owned=[p.value], opened=opened)
+
+    def close(self):
+        for q in self._opened:
+            lib().b200fa_peer_close(q)
+        for q in self._owned:
+            lib().b200fa_peer_free(q)
+        self._opened, self._owned = [], []
+
+
+def flash_attn_partial_scatter(q, k, v, xch: PeerExchange, mask=None, scale=None, kv_pos0=0, n_kv_total=None, flags=0,
+                               workspace: Workspace | None = None, stream=None, kv_type=None):
+    """This rank's (O~, m, l) triples -> its slot of every rank's exchange buffer, over NVLink stores (no NCCL)."""
+    qt, kt = _type_of(q), _type_of(k, kv_type)
+    q_ne, q_nb = _ne_nb(q, qt); k_ne, k_nb = _ne_nb(k, kt); _, v_nb = _ne_nb(v, kt)
+    D, n_q, n_head, n_b = q_ne
+    if scale is None:
+        scale = 1.0 / (D ** 0.5)
+    if n_kv_total is None:
+        n_kv_total = kv_pos0 + k_ne[1]
+    if workspace is None:
+        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+    m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
+    rc = lib().b200fa_flash_attn_partial_scatter(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, scale, qt, kt, *q_ne, *k_ne, ne31, nb31,
+        q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
+        xch.own_ptr, xch.peers_dev.data_ptr(), xch.rank, xch.world, flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_flash_attn_partial_scatter")
+
+
+def merge_partials_wait(xch: PeerExchange, dst=None, dst_dtype=None, stream=None):
+    """Waits on the device for all ranks' triples of the current step, then merges them -> dst [rows][D]."""
+    import torch
+    if dst is None:
+        dst = torch.empty((xch.rows, xch.D), dtype=dst_dtype or torch.float32, device="cuda")
+    rc = lib().b200fa_merge_partials_wait(xch.own_ptr, xch.world, xch.rows, xch.D, dst.data_ptr(), _type_of(dst), _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_merge_partials_wait")
+    return dst
+
+
+def flash_attn_seqpar(q, k, v, xch: PeerExchange, mask=None, scale=None, kv_pos0=0, n_kv_total=None, flags=0, dst=None, dst_dtype=None,
+                      workspace: Workspace | None = None, stream=None, kv_type=None):
+    """One sequence-parallel step in one call (one kernel for decode shapes): this rank's KV band -> dst [rows][D] on every rank."""
+    import torch
+    qt, kt = _type_of(q), _type_of(k, kv_type)
+    q_ne, q_nb = _ne_nb(q, qt); k_ne, k_nb = _ne_nb(k, kt); _, v_nb = _ne_nb(v, kt)
+    D, n_q, n_head, n_b = q_ne
+    if scale is None:
+        scale = 1.0 / (D ** 0.5)
+    if n_kv_total is None:
+        n_kv_total = kv_pos0 + k_ne[1]
+    if dst is None:
+        dst = torch.empty((n_b * n_q * n_head, D), dtype=dst_dtype or torch.float32, device=q.device)
+    if workspace is None:
+        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+    m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
+    rc = lib().b200fa_flash_attn_seqpar(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, _type_of(dst), *q_ne, *k_ne, ne31, nb31,
+        q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
+        xch.own_ptr, xch.peers_dev.data_ptr(), xch.rank, xch.world, flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_flash_attn_seqpar")
+    return dst

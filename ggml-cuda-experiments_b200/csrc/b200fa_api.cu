@@ -21,6 +21,9 @@ thread_local const char* g_last_dispatch = "none";
 thread_local int g_last_launches = 0;
 unsigned long long* g_timeline = nullptr;  // diagnostics: see b200fa_debug_timeline
 
+struct SeqPar { char* const* peers = nullptr; int rank = 0, world = 1; void* fdst = nullptr; int fdst_type = 0; };
+thread_local SeqPar g_seqpar;  // set by b200fa_flash_attn_seqpar around its attn_common call
+
 struct DeviceInfo {
     int sm_count = 0;
     int cc_major = 0;
@@ -189,7 +192,7 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
 int validate(const void* q, const void* k, const void* v, const void* out, int q_type, int kv_type, int dst_type,
              int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03, int64_t ne10, int64_t ne11, int64_t ne12,
              int64_t ne13, const void* mask, int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
-             int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23) {
+             int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23, bool out_is_partial = false) {
     if (!q || !k || !v || !out) return B200FA_ERR_INVALID;
     if (ne00 <= 0 || ne01 <= 0 || ne02 <= 0 || ne03 <= 0 || ne11 <= 0 || ne12 <= 0 || ne13 <= 0) return B200FA_ERR_INVALID;
     if (ne00 != ne10) return B200FA_ERR_INVALID;
@@ -212,7 +215,7 @@ int validate(const void* q, const void* k, const void* v, const void* out, int q
     if (mask) {
         if (ne31 < ne01 || nb31 < ne11 * 2 || ((uintptr_t)mask | nb31) % 2) return B200FA_ERR_INVALID;
     }
-    if ((uintptr_t)out % 16) return B200FA_ERR_INVALID;
+    if ((uintptr_t)out % (out_is_partial ? 8 : 16)) return B200FA_ERR_INVALID;  // triples are (D + 2) floats: 8-byte aligned rows
     return B200FA_OK;
 }
 
@@ -285,6 +288,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     a.rec = reinterpret_cast<float*>(ws + pl.ctr_bytes);
     a.timeline = g_timeline;
     a.cluster_k = pl.cluster_k;
+    a.peers = g_seqpar.peers; a.rank = g_seqpar.rank; a.world = g_seqpar.world; a.fdst = g_seqpar.fdst; a.fdst_type = g_seqpar.fdst_type;
     a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {
@@ -356,7 +360,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     g_last_launches = 0;
     const bool want_partial = partial_out != nullptr;
     int rc = validate(q, k, v, want_partial ? (void*)partial_out : dst, q_type, kv_type, dst_type, ne00, ne01, ne02,
-                      ne03, ne10, ne11, ne12, ne13, mask, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23);
+                      ne03, ne10, ne11, ne12, ne13, mask, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, want_partial);
     if (rc != B200FA_OK) return rc;
     const DeviceInfo& di = device_info();
     if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;  // sm_100a only, no fallback
@@ -443,6 +447,100 @@ int b200fa_flash_attn_partial(const void* q, const void* k, const void* v, const
                        ne10, ne11, ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0,
                        n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }
+
+size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D) {
+    if (world < 1 || n_rows < 1 || D < 1) return 0;
+    return (size_t)kXchgHeader + (1 + 2 * (size_t)world) * (size_t)n_rows * (size_t)(D + 2) * 4;
+}
+
+int b200fa_flash_attn_partial_scatter(const void* q, const void* k, const void* v, const void* mask, float scale,
+                                      int q_type, int kv_type,
+                                      int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                                      int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                                      int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                                      int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                                      int64_t kv_pos0, int64_t n_kv_total, void* xchg, void* const* peers, int rank, int world,
+                                      uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    if (!xchg || !peers || world < 1 || rank < 0 || rank >= world || ((uintptr_t)xchg % 256)) return B200FA_ERR_INVALID;
+    if (kv_pos0 < 0 || n_kv_total < kv_pos0 + ne11) return B200FA_ERR_INVALID;
+    const int64_t n_rows = ne03 * ne01 * ne02, n_floats = n_rows * (ne00 + 2);
+    float* staging = reinterpret_cast<float*>((char*)xchg + kXchgHeader);
+    int rc = attn_common(q, k, v, mask, nullptr, staging, scale, q_type, kv_type, B200FA_TYPE_F32, ne00, ne01, ne02, ne03,
+                         ne10, ne11, ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0,
+                         n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc != B200FA_OK) return rc;
+    unsigned blocks = (unsigned)((n_floats + 1023) / 1024);
+    if (blocks > 32) blocks = 32;
+    if (blocks < 1) blocks = 1;
+    fa_scatter_signal<<<blocks, 256, 0, (cudaStream_t)stream>>>((char* const*)peers, rank, world, n_floats);
+    g_last_launches++;
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+int b200fa_flash_attn_seqpar(const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+                             int q_type, int kv_type, int dst_type,
+                             int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                             int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                             int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                             int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                             int64_t kv_pos0, int64_t n_kv_total, void* xchg, void* const* peers, int rank, int world,
+                             uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    if (!dst || !xchg || !peers || world < 1 || rank < 0 || rank >= world || ((uintptr_t)xchg % 256) || ((uintptr_t)dst % 16)) return B200FA_ERR_INVALID;
+    if (dst_type != B200FA_TYPE_F32 && dst_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
+    if (kv_pos0 < 0 || n_kv_total < kv_pos0 + ne11) return B200FA_ERR_INVALID;
+    // one launch when the stream decode kernel takes the shape; otherwise the three-launch sequence
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
+    Shape sh{q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total};
+    const Plan pl = make_plan(sh, flags, di.sm_count, true, false);
+    if (pl.kind == kStream) {
+        float* staging = reinterpret_cast<float*>((char*)xchg + kXchgHeader);  // never written in this mode; only a non-null partial_out
+        g_seqpar.peers = (char* const*)peers; g_seqpar.rank = rank; g_seqpar.world = world; g_seqpar.fdst = dst; g_seqpar.fdst_type = dst_type;
+        const int rc = attn_common(q, k, v, mask, nullptr, staging, scale, q_type, kv_type, B200FA_TYPE_F32, ne00, ne01, ne02, ne03,
+                                   ne10, ne11, ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0,
+                                   n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+        g_seqpar = SeqPar{};
+        if (rc == B200FA_OK) g_last_dispatch = "decode_stream_seqpar";
+        return rc;
+    }
+    int rc = b200fa_flash_attn_partial_scatter(q, k, v, mask, scale, q_type, kv_type, ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13, ne31,
+                                               nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0, n_kv_total, xchg, peers, rank,
+                                               world, flags, workspace, workspace_bytes, stream);
+    if (rc != B200FA_OK) return rc;
+    return b200fa_merge_partials_wait(xchg, world, ne03 * ne01 * ne02, ne00, dst, dst_type, stream);
+}
+
+int b200fa_merge_partials_wait(void* xchg, int world, int64_t n_rows, int64_t D, void* dst, int dst_type, b200fa_stream_t stream) {
+    if (!xchg || !dst || world < 1 || n_rows < 1) return B200FA_ERR_INVALID;
+    if (dst_type != B200FA_TYPE_F32 && dst_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
+    const DeviceInfo& di = device_info();
+    if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
+    if (D == 128) fa_combine_wait<128><<<(unsigned)n_rows, 128, 0, (cudaStream_t)stream>>>((char*)xchg, world, n_rows, dst, dst_type);
+    else if (D == 64) fa_combine_wait<64><<<(unsigned)n_rows, 64, 0, (cudaStream_t)stream>>>((char*)xchg, world, n_rows, dst, dst_type);
+    else return B200FA_ERR_UNSUPPORTED;
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
+int b200fa_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
+    if (!ptr || !handle || bytes == 0) return B200FA_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return B200FA_ERR_CUDA;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return B200FA_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return B200FA_ERR_CUDA; }
+    memcpy(handle, &h, 64);
+    *ptr = p;
+    return B200FA_OK;
+}
+int b200fa_peer_open(const unsigned char handle[64], void** ptr) {
+    if (!ptr || !handle) return B200FA_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+int b200fa_peer_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA; }
+int b200fa_peer_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA; }
 
 int b200fa_workspace_init(void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
     if (!workspace || !workspace_bytes) return B200FA_ERR_INVALID;

@@ -684,4 +684,78 @@ __global__ void __launch_bounds__(D) fa_combine(const float* __restrict__ part, 
     else reinterpret_cast<float*>(dst)[row * D + d] = y;
 }
 
+// ---- cross-GPU combine over peer-mapped memory (NVLink stores), no NCCL on the path ----
+// Exchange buffer, identical on every rank (zero-filled once):
+//   header (256 B): [0] arrival counter (monotonic: += 1 per rank per step, written by every rank)
+//                   [16] scatter block counter, [17] merge block counter (self-resetting), [32] steps completed by THIS rank
+//   staging   [row][D + 2] f32 : this rank's triples of the current step (written by the attention kernel)
+//   gathered  [gen][rank][row][D + 2] f32 : two generations (step parity)
+// The step number lives on the device, so a step is a fixed sequence of launches that can be captured in a CUDA graph.
+constexpr int kXchgHeader = 256;
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Copies this rank's staged triples into slot `rank` of every rank's gathered area (its own included) with plain stores —
+// over NVLink for the peers — then publishes them: system-scope fence + one atomic increment of every arrival counter.
+__global__ void __launch_bounds__(256) fa_scatter_signal(char* const* __restrict__ peers, int rank, int world, int64_t n_floats) {
+    char* own = peers[rank];
+    unsigned int* hdr = reinterpret_cast<unsigned int*>(own);
+    const unsigned int step = hdr[32] + 1;                       // this rank's step in progress
+    const int64_t gen_off = (int64_t)(step & 1u) * world * n_floats;
+    const float* src = reinterpret_cast<const float*>(own + kXchgHeader);
+    for (int pr = 0; pr < world; pr++) {
+        float* dst = reinterpret_cast<float*>(peers[pr] + kXchgHeader) + n_floats + gen_off + (int64_t)rank * n_floats;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_floats; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicInc(hdr + 16, gridDim.x - 1) == gridDim.x - 1) {  // the last block to finish signals every rank
+            __threadfence_system();
+            for (int pr = 0; pr < world; pr++) atomicAdd_system(reinterpret_cast<unsigned int*>(peers[pr]), 1u);
+        }
+    }
+}
+
+// fa_combine that first waits until all `n_parts` ranks have published this rank's current step into its exchange buffer.
+template <int D>
+__global__ void __launch_bounds__(D) fa_combine_wait(char* __restrict__ xchg, int n_parts, int64_t n_rows, void* __restrict__ dst, int dst_type) {
+    unsigned int* hdr = reinterpret_cast<unsigned int*>(xchg);
+    const unsigned int step = hdr[32] + 1;
+    if (threadIdx.x == 0) {
+        const unsigned int want = step * (unsigned int)n_parts;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(hdr) - want) < 0) {
+            if (clock64() - t0 > 8000000000LL) __trap();  // a missing rank must not hang the GPU
+        }
+    }
+    __syncthreads();
+    const int64_t n_floats = n_rows * (D + 2);
+    const float* part = reinterpret_cast<const float*>(xchg + kXchgHeader) + n_floats + (int64_t)(step & 1u) * n_parts * n_floats;
+    const int64_t row = blockIdx.x;
+    const int d = threadIdx.x;
+    float M = -INFINITY;
+    for (int s = 0; s < n_parts; s++) M = fmaxf(M, __ldcv(part + ((int64_t)s * n_rows + row) * (D + 2) + D));
+    const float Mu = (M == -INFINITY) ? 0.f : M;
+    float L = 0.f, acc = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < n_parts; s++) {
+        const float* rec = part + ((int64_t)s * n_rows + row) * (D + 2);
+        const float wt = __expf(__ldcv(rec + D) - Mu);
+        L += __ldcv(rec + D + 1) * wt;
+        acc += __ldcv(rec + d) * wt;
+    }
+    const float y = L > 0.f ? acc / L : 0.f;
+    if (dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(dst)[row * D + d] = __float2half_rn(y);
+    else reinterpret_cast<float*>(dst)[row * D + d] = y;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicInc(hdr + 17, gridDim.x - 1) == gridDim.x - 1) hdr[32] = step;  // last block: the step is complete on this rank
+    }
+}
+
 }  // namespace b200fa

@@ -82,6 +82,12 @@ struct DkArgs {
     unsigned int* counters;  // [n_units], zero between calls
     int mask_bulk;           // mask rows can be staged with 128-byte bulk copies (16-byte aligned rows)
     unsigned long long* timeline;  // diagnostics: 8 globaltimer stamps per CTA, or null
+    // fused sequence-parallel step (b200fa_flash_attn_seqpar): the unit triples go straight into every rank's exchange buffer
+    // over NVLink, the last CTA of this rank waits for all ranks' arrivals and merges into fdst.  null = off.
+    char* const* peers;      // device array of `world` exchange-buffer pointers (peers[rank] = own)
+    int rank, world;
+    void* fdst;              // final merged output [rows][D]
+    int fdst_type;
     int cluster_k;           // > 1: the grid is launched in clusters of cluster_k CTAs = the CTAs of one unit; their records are
                              // merged through distributed shared memory (no global fence / atomic / L2 round trips)
 };
@@ -444,6 +450,71 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     const bool stamp = a.timeline != nullptr && threadIdx.x == 0;
     if (stamp) a.timeline[blockIdx.x * 8 + 0] = dk_now();
 
+    // ---- fused sequence-parallel step: where the unit triples go, and what the last CTA of the rank does ----
+    int units_done = 0;  // units whose final triple this CTA has written
+    unsigned int sp_step = 0;
+    int64_t sp_gen_off = 0;
+    const int64_t sp_n_floats = p.total_rows * (D + 2);
+    if (a.peers != nullptr) {
+        sp_step = reinterpret_cast<const unsigned int*>(a.peers[a.rank])[32] + 1;  // this rank's step in progress (see decode_mma.cuh)
+        sp_gen_off = (int64_t)(sp_step & 1u) * a.world * sp_n_floats;
+    }
+    auto emit_triple = [&](int64_t orow, int d, float acc, bool with_ml, float m_nat, float l_sum) {
+        const int64_t off = sp_n_floats + sp_gen_off + (int64_t)a.rank * sp_n_floats + orow * (D + 2);
+        for (int pr = 0; pr < a.world; pr++) {  // plain stores; over NVLink for the peers
+            float* out = reinterpret_cast<float*>(a.peers[pr] + kXchgHeader) + off;
+            out[d] = acc;
+            if (with_ml) { out[D] = m_nat; out[D + 1] = l_sum; }
+        }
+    };
+    auto finish_seqpar = [&]() {
+        if (a.peers == nullptr || units_done == 0) return;  // (uniform per CTA) only CTAs that published a unit have anything to do
+        unsigned int* hdr = reinterpret_cast<unsigned int*>(a.peers[a.rank]);
+        __threadfence_system();
+        bar_consumers();
+        if (threadIdx.x == 0) {
+            const unsigned int old = atomicAdd(hdr + 16, (unsigned int)units_done);
+            s_flag[2] = (int)old;
+            if (old + (unsigned int)units_done == (unsigned int)a.n_units) {  // every unit of this rank has been published
+                hdr[16] = 0u;
+                __threadfence_system();
+                for (int pr = 0; pr < a.world; pr++) atomicAdd_system(reinterpret_cast<unsigned int*>(a.peers[pr]), 1u);
+            }
+            // every publishing CTA waits for all ranks' arrivals, then merges its share of the output (fa_reduce algebra)
+            const unsigned int want = sp_step * (unsigned int)a.world;
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys(hdr) - want) < 0) {
+                if (clock64() - t0 > 8000000000LL) __trap();  // a missing rank must not hang the GPU
+            }
+        }
+        bar_consumers();
+        const int64_t n_out = p.total_rows * D;
+        const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;  // share ~ units published
+        const float* part = reinterpret_cast<const float*>(a.peers[a.rank] + kXchgHeader) + sp_n_floats + sp_gen_off;
+        for (int64_t idx = lo + threadIdx.x; idx < hi; idx += DK_CWARPS * 32) {
+            const int64_t row = idx / D;
+            const int d = (int)(idx % D);
+            float M = -INFINITY;
+            for (int s2 = 0; s2 < a.world; s2++) M = fmaxf(M, __ldcv(part + ((int64_t)s2 * p.total_rows + row) * (D + 2) + D));
+            const float Mu = (M == -INFINITY) ? 0.f : M;
+            float L = 0.f, acc = 0.f;
+            for (int s2 = 0; s2 < a.world; s2++) {
+                const float* rec = part + ((int64_t)s2 * p.total_rows + row) * (D + 2);
+                const float wt = __expf(__ldcv(rec + D) - Mu);
+                L += __ldcv(rec + D + 1) * wt;
+                acc += __ldcv(rec + d) * wt;
+            }
+            const float y = L > 0.f ? acc / L : 0.f;
+            if (a.fdst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(a.fdst)[row * D + d] = __float2half_rn(y);
+            else reinterpret_cast<float*>(a.fdst)[row * D + d] = y;
+        }
+        bar_consumers();
+        if (threadIdx.x == 0) {
+            const unsigned int done = atomicAdd(hdr + 17, (unsigned int)units_done);
+            if (done + (unsigned int)units_done == (unsigned int)a.n_units) { hdr[17] = 0u; hdr[32] = sp_step; }  // the step is complete on this rank
+        }
+    };
+
     int i = 0, slot_idx = 0;
     int n_def = 0, def_u[2] = {0, 0}, def_c0[2] = {0, 0}, def_n[2] = {0, 0};  // partial units of this CTA (at most the first and the last segment)
     int cl_u = 0, cl_n = 1;  // cluster mode: the CTA's single unit and its contributor count
@@ -571,6 +642,8 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                     const float y = L > 0.f ? acc / L : 0.f;
                     if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
                     else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                } else if (a.peers != nullptr) {
+                    emit_triple(orow, d, acc, first, M * kLn2, L);
                 } else {
                     float* out = p.part_out + orow * (D + 2);
                     out[d] = acc;
@@ -578,6 +651,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 }
             }
         }
+        if (n_contrib == 1) units_done++;
         if (stamp) a.timeline[blockIdx.x * 8 + 3] = dk_now();
         // Units shared with other CTAs are signalled and merged after the CTA's whole run (below): only its first and its
         // last segment can be partial units, and a fence + atomic round trip in the middle of the stream would stall the
@@ -593,7 +667,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     if (a.cluster_k > 1) {
         // ---- cluster mode: the unit's CTAs are one thread-block cluster; their records sit in the leader's shared memory ----
         cluster_sync_all();
-        if (blockIdx.x % a.cluster_k != 0 || cl_n <= 1) return;
+        if (blockIdx.x % a.cluster_k != 0 || cl_n <= 1) { finish_seqpar(); return; }
         const int u = cl_u, n_contrib = cl_n;
         const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
         const float* recs = reinterpret_cast<const float*>(smem);
@@ -614,13 +688,17 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 const float y = L > 0.f ? acc / L : 0.f;
                 if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
                 else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+            } else if (a.peers != nullptr) {
+                emit_triple(orow, d, acc, d == 0, M * kLn2, L);
             } else {
                 float* out = p.part_out + orow * (D + 2);
                 out[d] = acc;
                 if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
             }
         }
+        units_done++;
         if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; }
+        finish_seqpar();
         return;
     }
 
@@ -629,6 +707,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     //      here one parallel fp32 pass) ----
     if (n_def == 0) {
         if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; }
+        finish_seqpar();
         return;
     }
     __threadfence();
@@ -681,13 +760,17 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 const float y = L > 0.f ? acc / L : 0.f;
                 if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
                 else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+            } else if (a.peers != nullptr) {
+                emit_triple(orow, d, acc, d == 0, M * kLn2, L);
             } else {
                 float* out = p.part_out + orow * (D + 2);
                 out[d] = acc;
                 if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
             }
         }
+        units_done++;
     }
+    finish_seqpar();
     if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; unsigned sm_id; asm("mov.u32 %0, %%smid;" : "=r"(sm_id)); a.timeline[blockIdx.x * 8 + 6] = sm_id; }
 }
 

@@ -77,9 +77,18 @@ def flash_attn_ext_head_parallel(q, k, v, mask, rank: int, world: int, attn_fn=N
 
 
 def flash_attn_ext_seq_parallel(q, k_local, v_local, mask_local, n_kv_total: int, rank: int, world: int, group=None,
-                                partial_fn=None, merge_fn=None, flags: int = 0, scale=None, **kw):
+                                partial_fn=None, merge_fn=None, flags: int = 0, scale=None, exchange=None, **kw):
     """dst [rows][D] on every rank.  `k_local`, `v_local` hold this rank's band seq_shard(n_kv_total, rank, world) of the
-    KV rows; `mask_local` (or None) the matching columns of the mask.  One all-gather of the (O~, m, l) triples."""
+    KV rows; `mask_local` (or None) the matching columns of the mask.  One all-gather of the (O~, m, l) triples — over NCCL,
+    or, with `exchange` (an api.PeerExchange of all ranks), over peer-mapped memory: NVLink stores from the attention kernel,
+    a device-side wait and the merge, in one launch for decode shapes (b200fa_flash_attn_seqpar)."""
+    if exchange is not None:
+        from .api import flash_attn_seqpar
+        sh = seq_shard(n_kv_total, rank, world)
+        if k_local.shape[2] != sh.n_local or sh.n_local == 0:
+            raise ValueError("the peer-memory path needs a non-empty band per rank")
+        return flash_attn_seqpar(q, k_local, v_local, exchange, mask=mask_local, scale=scale, kv_pos0=sh.kv_pos0, n_kv_total=n_kv_total,
+                                 flags=flags, **kw)
     import torch
     import torch.distributed as dist
     if partial_fn is None or merge_fn is None:

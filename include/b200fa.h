@@ -130,6 +130,54 @@ int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, in
                           void* dst, int dst_type, b200fa_stream_t stream);
 
 /*
+ * Sequence-split combine over peer-mapped memory (NVLink 5 / NVSwitch), without NCCL on the path.
+ * Every rank owns an *exchange buffer* of b200fa_xchg_bytes(world, n_rows, D) bytes, zero-filled once, mapped into every
+* peer (cudaIpc: b200fa_peer_alloc / b200fa_peer_open below, or any other peer mapping).  `xchg` is this rank's own buffer,
+ * `peers` a DEVICE array of `world` pointers to all ranks' buffers as seen from this rank (peers[rank] == xchg).  Per step
+ * (the step number is kept on the device, so the pair of calls is a fixed launch sequence that a CUDA graph can replay):
+ *   b200fa_flash_attn_partial_scatter : like b200fa_flash_attn_partial, but the triples go into this rank's slot of its
+ *        own exchange buffer and are then stored into the same slot of every peer's buffer (plain NVLink stores), followed
+ *        by a system-scope fence and one atomic increment of each peer's arrival counter;
+*   b200fa_merge_partials_wait        : waits (on the device) until all `world` ranks have published this step, then merges
+ *        (fa_reduce algebra) into dst.  Bounded wait: traps after ~4 s instead of hanging.
+ * Two generations of the gathered area (step parity) make it safe for a fast rank to start the next step early.
+ */
+size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D);
+int b200fa_flash_attn_partial_scatter(
+    const void* q, const void* k, const void* v, const void* mask, float scale,
+    int q_type, int kv_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t kv_pos0, int64_t n_kv_total,
+    void* xchg, void* const* peers, int rank, int world,
+    uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
+int b200fa_merge_partials_wait(void* xchg, int world, int64_t n_rows, int64_t D, void* dst, int dst_type, b200fa_stream_t stream);
+/* The whole sequence-parallel step in one call — and, for decode shapes (<= 16 rows per KV head), in ONE kernel: the stream
+ * decode kernel stores each unit's triple straight into every rank's exchange buffer over NVLink; the last CTA of the rank
+ * signals the peers, waits for their arrivals and merges into dst [rows][D].  dst holds the same result on every rank. */
+int b200fa_flash_attn_seqpar(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t kv_pos0, int64_t n_kv_total,
+    void* xchg, void* const* peers, int rank, int world,
+    uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
+/* cudaMalloc'd, zero-filled buffer + its cudaIpc handle (64 bytes) / mapping of a peer's handle / release. */
+int b200fa_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int b200fa_peer_open(const unsigned char handle[64], void** ptr);
+int b200fa_peer_close(void* ptr);
+int b200fa_peer_free(void* ptr);
+
+/*
  * ggml q8_0 rows (block {f16 d; int8 qs[32]}, 34 bytes).  Not in the reference;
  * format and rounding are ggml's published ones.  n_elements % 32 == 0.
  *   quantize : d = amax/127 (stored f16), q = roundf(x * (1/d))       src f32 or f16

@@ -286,3 +286,54 @@ def test_kv_cache_append_then_decode(q8):
     out = P.flash_attn_ext(to_dev(Q), kc[:, :, :n], vc[:, :, :n], None, kv_type=P.TYPE_Q8_0 if q8 else None)
     torch.cuda.synchronize()
     assert_close(out.cpu().numpy(), ref, "decode over the appended cache")
+
+
+# ---- sequence-split combine over peer-mapped memory (no NCCL): `world` ranks emulated on one device ----
+@pytest.mark.parametrize("world,q8", [(1, False), (2, False), (4, True), (8, False)])
+def test_peer_exchange_combine_emulated_ranks(world, q8):
+    import torch
+    P = pkg()
+    n_kv, H, Hk, D = 4096, 32, 8, 128
+    Q, K, V = synth_qkv(D, 1, n_kv, H, Hk)
+    if q8:
+        Kq, Vq = oracle.quantize_q8_0(K.astype(np.float32)), oracle.quantize_q8_0(V.astype(np.float32))
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(Kq, 8), oracle.view_of(Vq, 8), None, 1 / np.sqrt(D), round_q_f16=True)
+        k, v = to_dev(Kq), to_dev(Vq)
+    else:
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), None, 1 / np.sqrt(D), round_q_f16=True)
+        k, v = to_dev(K), to_dev(V)
+    q = to_dev(Q)
+    xs = P.PeerExchange.local(world, H, D)
+    try:
+        for epoch in (1, 2, 3):  # three steps: both generations of the gathered area and the monotonic counters
+            for r in range(world):
+                sh = P.seq_shard(n_kv, r, world)
+                P.flash_attn_partial_scatter(q, k[:, :, sh.kv_pos0:sh.kv_pos0 + sh.n_local], v[:, :, sh.kv_pos0:sh.kv_pos0 + sh.n_local], xs[r],
+                                             kv_pos0=sh.kv_pos0, n_kv_total=n_kv)
+            for r in range(world):
+                out = P.merge_partials_wait(xs[r])
+                torch.cuda.synchronize()
+                assert_close(out.cpu().numpy().reshape(ref.shape), ref, f"peer exchange world={world} rank={r} epoch={epoch}")
+    finally:
+        for x in xs:
+            x.close()
+
+
+def test_fused_seqpar_step_world_1():
+    """The one-kernel sequence-parallel step (decode + NVLink scatter + arrival wait + merge).  On one GPU only world = 1 can
+    run it (a rank waits for its peers inside the kernel); tests/multi_gpu_check.py runs it on real peers."""
+    import torch
+    P = pkg()
+    n_kv, H, Hk, D = 3000, 32, 8, 128
+    Q, K, V = synth_qkv(D, 1, n_kv, H, Hk)
+    ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), None, 1 / np.sqrt(D), round_q_f16=True)
+    q, k, v = to_dev(Q), to_dev(K), to_dev(V)
+    xs = P.PeerExchange.local(1, H, D)
+    try:
+        for step in range(3):
+            out = P.flash_attn_seqpar(q, k, v, xs[0])
+            torch.cuda.synchronize()
+            assert P.last_dispatch() == "decode_stream_seqpar" and P.last_launch_count() == 1
+            assert_close(out.cpu().numpy().reshape(ref.shape), ref, f"fused seqpar step {step}")
+    finally:
+        xs[0].close()
