@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libb200fa.so")
 SOURCES = ["b200fa_api.cu"]
-HEADERS = ["common.cuh", "decode_mma.cuh", "prefill_tcgen05.cuh", "prefill_persistent.cuh", "prefill_persistent2.cuh", "decode_stream.cuh", "sm100_ptx.cuh", "q8_0.cuh", "../../include/b200fa.h"]
+HEADERS = ["common.cuh", "decode_mma.cuh", "prefill_tcgen05.cuh", "prefill_persistent.cuh", "prefill_persistent2.cuh", "decode_stream.cuh", "sm100_ptx.cuh", "q8_0.cuh", "tensor_file.cuh", "../../include/b200fa.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

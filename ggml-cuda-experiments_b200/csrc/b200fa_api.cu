@@ -12,6 +12,7 @@
 #include "prefill_persistent.cuh"
 #include "prefill_persistent2.cuh"
 #include "q8_0.cuh"
+#include "tensor_file.cuh"
 
 using namespace b200fa;
 
@@ -316,11 +317,17 @@ const char* b200fa_status_string(int s) {
         case B200FA_ERR_UNSUPPORTED: return "unsupported shape or type";
         case B200FA_ERR_WORKSPACE: return "workspace missing or too small";
         case B200FA_ERR_CUDA: return "no sm_100 device or launch failed";
+        case B200FA_ERR_IO: return "tensor file missing, truncated or not writable";
         default: return "unknown status";
     }
 }
 
 int b200fa_version(void) { return 100; }
+int b200fa_tensor_file_info(const char* path, b200fa_tensor_info* info) { return tf_info(path, info); }
+int b200fa_tensor_file_read(const char* path, void* dst, size_t dst_bytes) { return tf_read(path, dst, dst_bytes); }
+int b200fa_tensor_file_write(const char* path, const char* name, int type, int n_dims, const int64_t* ne, const void* data) {
+    return tf_write(path, name, type, n_dims, ne, data);
+}
 void b200fa_debug_set(void* timeout_word, float* dump, int dump_cta) {
     pf_debug().dbg = (unsigned long long*)timeout_word;
     pf_debug().dump = dump;

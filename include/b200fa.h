@@ -51,6 +51,7 @@ extern "C" {
 #define B200FA_ERR_UNSUPPORTED (-2)  /* valid but not built: head size, type combination */
 #define B200FA_ERR_WORKSPACE (-3)    /* workspace NULL or smaller than b200fa_workspace_size() */
 #define B200FA_ERR_CUDA (-4)         /* no sm_100 device, or the launch itself failed */
+#define B200FA_ERR_IO (-5)           /* tensor-dump file missing, unreadable, truncated or not writable */
 
 typedef void* b200fa_stream_t; /* a cudaStream_t */
 
@@ -196,6 +197,26 @@ int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n_elements, b200
 int b200fa_kv_cache_append(const void* src, int src_type, void* cache, int cache_type, int64_t D, int64_t n_tokens,
                            int64_t n_head_kv, int64_t n_batch, int64_t src_nb1, int64_t src_nb2, int64_t src_nb3,
                            int64_t cache_nb1, int64_t cache_nb2, int64_t cache_nb3, int64_t n_past, b200fa_stream_t stream);
+
+/*
+ * ggml tensor-dump files (host side, no GPU involved): the fixture format the reference replays
+ * (loader: utils.h:110-150; use: flash-matrix.cu:69-73, files fa-cuda-{q,k,v,mask,qkv}-256.tensor).
+ *   i32 n_dims | i32 type (0 f32, 1 f16) | i32 ne[n_dims] | i32 name_len | name | raw data (ne[0] fastest)
+ * _info parses the header and checks that the whole payload is present; _read copies the payload into `dst`
+ * (host memory, >= data_bytes); _write produces a file the reference's loader accepts (name <= 19 chars, its
+ * field is char[20]).
+ */
+typedef struct b200fa_tensor_info {
+    int32_t n_dims;
+    int32_t type;         /* B200FA_TYPE_F32 | B200FA_TYPE_F16 */
+    int64_t ne[4];        /* unused trailing dimensions are 1 */
+    char name[64];
+    int64_t data_offset;  /* byte offset of the payload in the file */
+    int64_t data_bytes;
+} b200fa_tensor_info;
+int b200fa_tensor_file_info(const char* path, b200fa_tensor_info* info);
+int b200fa_tensor_file_read(const char* path, void* dst, size_t dst_bytes);
+int b200fa_tensor_file_write(const char* path, const char* name, int type, int n_dims, const int64_t* ne, const void* data);
 
 /* Diagnostics: name of the kernel family the last b200fa_flash_attn_ext call on this thread dispatched to
  * ("decode_splitkv", "prefill_tcgen05", "rows16_mma"), and how many kernels it launched. */

@@ -55,6 +55,9 @@ def ref_host() -> C.CDLL:
     l.ref_host_attention_llama.argtypes = [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_float, C.c_int]
     l.ref_host_attention_ktest.restype = C.c_int
     l.ref_host_attention_ktest.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_float]
+    if hasattr(l, "ref_host_load_tensor"):
+        l.ref_host_load_tensor.restype = C.c_int
+        l.ref_host_load_tensor.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_void_p, C.c_int64]
     return l
 
 

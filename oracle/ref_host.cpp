@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <thread>
 #include <vector>
 #include "utils.h"
@@ -60,6 +61,19 @@ int ref_host_attention_ktest(const float* query, const float* key, const float* 
     }
     for (int h = 0; h < n_head; h++)
         mulmat_cpu(scores + (size_t)h * n_kv, value + (size_t)(h / r) * D * n_kv, nullptr, qkv + h * D, 1, D, n_kv, 1.0f);
+    return 0;
+}
+
+// utils.h:110-150 — the reference's own tensor-dump loader, used to check that files written by the product's writer
+// load there.  The loader does not return ne, so the caller says how many payload bytes to copy out.
+int ref_host_load_tensor(const char* path, int* type, char* name20, void* dst, int64_t bytes) {
+    tensor* t = load_tensor_from_file(path);
+    if (!t) return -1;
+    *type = t->type;
+    memcpy(name20, t->name, 20);
+    memcpy(dst, t->data, (size_t)bytes);
+    free(t->data);
+    delete t;
     return 0;
 }
 
