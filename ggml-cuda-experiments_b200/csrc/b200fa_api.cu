@@ -77,6 +77,7 @@ struct Shape {
     int64_t nb11, nb12, nb13, nb21, nb22, nb23;  // 0 = unknown (workspace sizing): assume the widest plan
     const void* k; const void* v;
     int64_t kv_pos0, n_kv_total;
+    int64_t Dr = 0;  // real head size when it differs from the structural D (0 = same)
 };
 
 bool stream_eligible(const Shape& sh, bool sizing) {
@@ -97,10 +98,10 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     const int64_t D = sh.D, n_q = sh.n_q, n_head = sh.n_head, n_batch = sh.n_batch, n_kv = sh.n_kv, n_head_kv = sh.n_head_kv;
     const int64_t gqa = n_head / n_head_kv;
     const int64_t rows = n_q * gqa;
-    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D == 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64 &&
-        n_kv <= (int64_t)PF_MAX_KV_TILES * PF_BN) {
+    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D <= 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64 &&
+        n_kv <= (sh.Dr == 0 || sh.Dr == 128 ? (int64_t)PF_MAX_KV_TILES * PF_BN : (int64_t)PP_MAX_KV_TILES * PF_BN)) {
         pl.kind = kPrefill;
-        if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * D * 2), 256);
+        if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * 128 * 2), 256);
         const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;
         pl.cls_bytes = align_up((size_t)(qt * kt), 256);
         pl.ctr_bytes = kCtrRegion;
@@ -201,7 +202,10 @@ int validate(const void* q, const void* k, const void* v, const void* out, int q
     if (q_type != B200FA_TYPE_F32 && q_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
     if (kv_type != B200FA_TYPE_F16 && kv_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
     if (dst_type != B200FA_TYPE_F32 && dst_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
-    if (ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
+    // f16 K/V: any head size that is a multiple of 8 up to 128 (80, 96, 112 ... run zero-padded on the 64/128 kernels);
+    // q8_0 K/V and the partial (sequence-split) entries: 64 or 128 only
+    if (ne00 % 8 || ne00 > 128) return B200FA_ERR_UNSUPPORTED;
+    if ((kv_type == B200FA_TYPE_Q8_0 || out_is_partial) && ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
     if (ne11 > 0x7fffffff || ne01 > 0x7fffffff || ne02 > 65535 || ne03 * ne12 > 65535) return B200FA_ERR_UNSUPPORTED;
     const int64_t qrow = ne00 * (q_type == B200FA_TYPE_F32 ? 4 : 2);
     if (nb01 < qrow || ((uintptr_t)q | nb01 | nb02 | nb03) % 16) return B200FA_ERR_INVALID;
@@ -293,8 +297,8 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {
-        if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.D)) return B200FA_ERR_CUDA;
-        if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.D)) return B200FA_ERR_CUDA;
+        if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
+        if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
     }
     const bool q8 = p.kv_type == B200FA_TYPE_Q8_0;
     static const int force_rh = getenv("B200FA_STREAM_RH") ? atoi(getenv("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
@@ -343,7 +347,8 @@ size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01
     const int sms = di.ok ? di.sm_count : 148;
     if (ne12 <= 0 || ne02 % ne12 || ne00 <= 0 || ne01 <= 0 || ne03 <= 0 || ne11 <= 0) return 0;
     (void)ne13;
-    Shape sh{q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11};
+    if (ne00 > 128) return 0;
+    Shape sh{q_type, kv_type, ne00 <= 64 ? 64 : 128, ne01, ne02, ne03, ne11, ne12, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11, ne00};
     size_t m = 0;
     for (int variant = 0; variant < 5; variant++) {  // every path the two entry points can take for this shape
         const bool partial = variant == 1 || variant == 3;
@@ -373,7 +378,8 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;  // sm_100a only, no fallback
 
     if (!(scale > 0.f)) flags |= B200FA_FLAG_NO_TCGEN05;  // the tile kernel takes row maxima of raw scores
-    Shape sh{q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total};
+    const int64_t Dp = ne00 <= 64 ? 64 : 128;  // structural head size of the decode kernels; the prefill kernel is always 128 wide
+    Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00};
     Plan pl = make_plan(sh, flags, di.sm_count, want_partial, false);
     if (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256)) return B200FA_ERR_WORKSPACE;
     char* ws = (char*)workspace;
@@ -383,7 +389,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.dst = dst; p.part = nullptr;
     p.scale = scale; p.scale_log2 = scale * kLog2e;
     p.q_type = q_type; p.kv_type = kv_type; p.dst_type = dst_type;
-    p.D = (int)ne00; p.n_q = (int)ne01; p.n_head = (int)ne02; p.n_batch = (int)ne03;
+    p.D = (int)Dp; p.Dr = (int)ne00; p.n_q = (int)ne01; p.n_head = (int)ne02; p.n_batch = (int)ne03;
     p.n_kv = (int)ne11; p.n_head_kv = (int)ne12; p.n_batch_kv = (int)ne13;
     p.gqa = (int)(ne02 / ne12); p.rk3 = (int)(ne03 / ne13);
     p.nb01 = nb01; p.nb02 = nb02; p.nb03 = nb03;
@@ -398,9 +404,10 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
 
     if (pl.kind == kPrefill) {
         g_last_dispatch = "prefill_tcgen05";
+        p.D = PF_D;
         int launches = 0;
         static const bool per_cta = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "cta");
-        if (per_cta || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
+        if ((per_cta && p.Dr == PF_D) || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
             rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
         } else {
             if (!(flags & B200FA_FLAG_WORKSPACE_ZEROED) && cudaMemsetAsync(ws + kPrefillCtrOff, 0, 256, st) != cudaSuccess) return B200FA_ERR_CUDA;

@@ -27,7 +27,8 @@ struct FaParams {
     float scale;       // as passed by the caller
     float scale_log2;  // scale * log2(e)
     int q_type, kv_type, dst_type;
-    int D, n_q, n_head, n_batch;
+    int D, n_q, n_head, n_batch;  // D: the head size the kernel is BUILT for (64 or 128; the data is zero-padded up to it on the fly)
+    int Dr;            // the real head size ne00 (multiple of 8, <= D): extent of Q/K/V/dst rows in memory
     int n_kv, n_head_kv, n_batch_kv;
     int gqa;           // rk2 = n_head / n_head_kv   (flash-llama.h:128)
     int rk3;           // n_batch / n_batch_kv       (flash-llama.h:129)

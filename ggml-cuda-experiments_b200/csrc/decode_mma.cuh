@@ -47,6 +47,10 @@ struct FifoGeom {
 __device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
 }
+// src_bytes = 16 copies, 0 writes 16 zero bytes without touching gmem (columns past the real head size)
+__device__ __forceinline__ void cp_async16z(uint32_t smem, const void* gmem, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async8(uint32_t smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
 }
@@ -157,7 +161,7 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
 #pragma unroll
         for (int c = 0; c < NC4; c++) {
             const int e0 = 8 * (t + 4 * c);
-            if (!rvalid[h]) {
+            if (!rvalid[h] || e0 >= p.Dr) {  // dead row, or a column past the real head size (zero padding)
                 qa[c][h][0] = qa[c][h][1] = qa[c][h][2] = qa[c][h][3] = 0u;
             } else if (p.q_type == B200FA_TYPE_F16) {
                 const uint4 x = *reinterpret_cast<const uint4*>(qrow + e0 * 2);
@@ -214,6 +218,15 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
     for (int h = 0; h < RH; h++) mlane[h] = p.mask ? mrow[h] + (int64_t)(kv_first + 4 * t) * 2 : nullptr;
     const int64_t kstep = (int64_t)kStrideKV * p.nb11, vstep = (int64_t)kStrideKV * p.nb21;
 
+    // Head sizes below D (p.Dr, f16 K/V only): this lane's 16-byte chunks that start past the real row end are never read from
+    // memory; they are fed as zeros (K: a zero column adds nothing to the score; V: those output columns are never stored).
+    bool kcol[NC4], vcol[NCV];
+#pragma unroll
+    for (int c = 0; c < NC4; c++) kcol[c] = Q8 || 8 * (t + 4 * c) < p.Dr;
+#pragma unroll
+    for (int c = 0; c < NCV; c++) vcol[c] = Q8 || (64 * c + 8 * g) < p.Dr;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
     // full tile (all 16 keys exist): loads through the running pointers, then advances them
     auto load_tile = [&](Tile& T) {
 #pragma unroll
@@ -221,7 +234,7 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
 #pragma unroll
             for (int c = 0; c < NC4; c++) {
                 if constexpr (!Q8) {
-                    const uint4 x = ld_nc_v4(klane[nt] + (t + 4 * c) * 16);
+                    const uint4 x = kcol[c] ? ld_nc_v4(klane[nt] + (t + 4 * c) * 16) : zero4;
                     T.kf[nt][c][0] = x.x; T.kf[nt][c][1] = x.y; T.kf[nt][c][2] = x.z; T.kf[nt][c][3] = x.w;
                 } else {
                     const uint2 w = ld_q8x8(klane[nt] + c * kQ8BlockBytes + 2 + 8 * t, al8);
@@ -234,7 +247,7 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
 #pragma unroll
             for (int c = 0; c < NCV; c++) {
                 if constexpr (!Q8) {
-                    const uint4 x = ld_nc_v4(vlane[i] + (64 * c + 8 * g) * 2);
+                    const uint4 x = vcol[c] ? ld_nc_v4(vlane[i] + (64 * c + 8 * g) * 2) : zero4;
                     T.vf[i][c][0] = x.x; T.vf[i][c][1] = x.y; T.vf[i][c][2] = x.z; T.vf[i][c][3] = x.w;
                 } else {
                     const char* b = vlane[i] + (2 * c + (g >> 2)) * kQ8BlockBytes;
@@ -277,11 +290,11 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-            for (int c = 0; c < NC4; c++) cp_async16(sb + (j++) * 512, klane[nt] + (t + 4 * c) * 16);
+            for (int c = 0; c < NC4; c++) cp_async16z(sb + (j++) * 512, klane[nt] + (t + 4 * c) * 16, kcol[c] ? 16u : 0u);
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int c = 0; c < NCV; c++) cp_async16(sb + (j++) * 512, vlane[i] + (64 * c + 8 * g) * 2);
+            for (int c = 0; c < NCV; c++) cp_async16z(sb + (j++) * 512, vlane[i] + (64 * c + 8 * g) * 2, vcol[c] ? 16u : 0u);
         if (mask_al8) {
 #pragma unroll
             for (int h = 0; h < RH; h++) {
@@ -333,7 +346,7 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
 #pragma unroll
             for (int c = 0; c < NC4; c++) {
                 if constexpr (!Q8) {
-                    const uint4 x = ld_nc_v4(kr + (t + 4 * c) * 16);
+                    const uint4 x = kcol[c] ? ld_nc_v4(kr + (t + 4 * c) * 16) : zero4;
                     T.kf[nt][c][0] = x.x; T.kf[nt][c][1] = x.y; T.kf[nt][c][2] = x.z; T.kf[nt][c][3] = x.w;
                 } else {
                     const uint2 w = ld_q8x8(kr + c * kQ8BlockBytes + 2 + 8 * t, false);
@@ -348,7 +361,7 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
 #pragma unroll
             for (int c = 0; c < NCV; c++) {
                 if constexpr (!Q8) {
-                    const uint4 x = ld_nc_v4(vr + (64 * c + 8 * g) * 2);
+                    const uint4 x = vcol[c] ? ld_nc_v4(vr + (64 * c + 8 * g) * 2) : zero4;
                     T.vf[i][c][0] = x.x; T.vf[i][c][1] = x.y; T.vf[i][c][2] = x.z; T.vf[i][c][3] = x.w;
                 } else {
                     const char* b = vr + (2 * c + (g >> 2)) * kQ8BlockBytes;
@@ -602,8 +615,10 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
         if (p.n_splits == 1) {
             if (p.dst != nullptr) {
                 const float y = L > 0.f ? acc / L : 0.f;
-                if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
-                else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                if (d < p.Dr) {
+                    if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
+                    else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+                }
             } else {
                 float* rec = p.part_out + orow * (D + 2);
                 rec[d] = acc;
@@ -650,8 +665,10 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
         }
         if (p.dst != nullptr) {
             const float y = L > 0.f ? acc / L : 0.f;
-            if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
-            else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+            if (d < p.Dr) {
+                if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
+                else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+            }
         } else {
             float* out = p.part_out + orow * (D + 2);
             out[d] = acc;

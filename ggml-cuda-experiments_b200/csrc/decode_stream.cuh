@@ -534,7 +534,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 #pragma unroll
             for (int c = 0; c < NC4; c++) {
                 const int e0 = 8 * (t + 4 * c);
-                if (!rvalid[h]) {
+                if (!rvalid[h] || e0 >= p.Dr) {  // dead row, or a column past the real head size (zero padding)
                     qa[c][h][0] = qa[c][h][1] = qa[c][h][2] = qa[c][h][3] = 0u;
                 } else if (p.q_type == B200FA_TYPE_F16) {
                     const uint4 v = *reinterpret_cast<const uint4*>(qrow + e0 * 2);
@@ -640,8 +640,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                     if (first) { rec[D] = M; rec[D + 1] = L; }  // log2 units inside the kernel
                 } else if (p.dst != nullptr) {
                     const float y = L > 0.f ? acc / L : 0.f;
-                    if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
-                    else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                    if (d < p.Dr) {
+                        if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
+                        else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+                    }
                 } else if (a.peers != nullptr) {
                     emit_triple(orow, d, acc, first, M * kLn2, L);
                 } else {
@@ -686,8 +688,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
             if (p.dst != nullptr) {
                 const float y = L > 0.f ? acc / L : 0.f;
-                if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
-                else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                if (d < p.Dr) {
+                    if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
+                    else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+                }
             } else if (a.peers != nullptr) {
                 emit_triple(orow, d, acc, d == 0, M * kLn2, L);
             } else {
@@ -758,8 +762,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
             if (p.dst != nullptr) {
                 const float y = L > 0.f ? acc / L : 0.f;
-                if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * D + d] = __float2half_rn(y);
-                else reinterpret_cast<float*>(p.dst)[orow * D + d] = y;
+                if (d < p.Dr) {
+                    if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
+                    else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+                }
             } else if (a.peers != nullptr) {
                 emit_triple(orow, d, acc, d == 0, M * kLn2, L);
             } else {

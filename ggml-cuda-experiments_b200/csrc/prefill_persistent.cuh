@@ -455,7 +455,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                 // clipped by the tensor map, and the warp only waits until the engine has READ the staging buffer.
                 const bool f32out = p.dst_type == B200FA_TYPE_F32;
                 const int row0 = q0 + (warp & 3) * 32;
-                const int n_pass = f32out ? 8 : 4;        // 16 f32 or 32 f16 columns = 64 bytes per pass
+                const int n_pass = (p.Dr * (f32out ? 4 : 2) + 63) >> 6;  // 16 f32 or 32 f16 columns = 64 bytes per pass; columns past the real head size are never stored
 #pragma unroll
                 for (int pass = 0; pass < 8; pass++) {
                     if (pass >= n_pass) break;

@@ -300,17 +300,21 @@ fa_prefill_persistent2(const __grid_constant__ FaParams p, const __grid_constant
 inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_bytes, unsigned int* counters, int sm_count,
                                      cudaStream_t st, int* launches) {
     if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PP_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
+    // Head sizes below 128 (Dr, a multiple of 8) run on the same 128-wide kernel: the tensor maps describe rows of Dr elements,
+    // so TMA zero-fills columns Dr..127 of every Q/K/V tile on the way in (zeros add nothing to Q.K^T, and the P.V columns they
+    // produce are never stored: the dst tensor map clips them on the way out).
+    const int Dr = p.Dr;
     int n = 0;
     const void* qbase = p.q;
     int64_t qnb1 = p.nb01, qnb2 = p.nb02, qnb3 = p.nb03;
     if (p.q_type == B200FA_TYPE_F32) {
         __half* q16 = reinterpret_cast<__half*>(ws);
-        const int64_t work = p.total_rows * (PF_D / 8);
-        fa_q_to_f16<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p.q, q16, PF_D, p.n_q, p.n_head, p.total_rows, p.nb01, p.nb02,
+        const int64_t work = p.total_rows * (Dr / 8);
+        fa_q_to_f16<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p.q, q16, Dr, p.n_q, p.n_head, p.total_rows, p.nb01, p.nb02,
                                                                    p.nb03);
         n++;
         qbase = q16;
-        qnb1 = PF_D * 2; qnb2 = (int64_t)p.n_q * PF_D * 2; qnb3 = (int64_t)p.n_head * p.n_q * PF_D * 2;
+        qnb1 = Dr * 2; qnb2 = (int64_t)p.n_q * Dr * 2; qnb3 = (int64_t)p.n_head * p.n_q * Dr * 2;
     }
     PpArgs pa{};
     PfArgs& a = pa.f;
@@ -329,17 +333,17 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     pa.n_items = a.n_q_pairs * p.n_head * p.n_batch;
     pa.counters = counters;
     CUtensorMap tq, tk, tv;
-    if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3)) return B200FA_ERR_CUDA;
-    if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13)) return B200FA_ERR_CUDA;
-    if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23)) return B200FA_ERR_CUDA;
+    if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3, 128, Dr)) return B200FA_ERR_CUDA;
+    if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, 128, Dr)) return B200FA_ERR_CUDA;
+    if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, 128, Dr)) return B200FA_ERR_CUDA;
     CUtensorMap to;
     {   // dst [batch][n_q][n_head][D]: box = 64 bytes x 1 head x 32 rows, 64-byte swizzle (the epilogue's staging layout)
         PFN_encodeTiled enc = get_encode_tiled();
         if (!enc) return B200FA_ERR_CUDA;
         const bool f32o = p.dst_type == B200FA_TYPE_F32;
         const cuuint64_t es = f32o ? 4 : 2;
-        cuuint64_t dims[4] = {(cuuint64_t)PF_D, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch};
-        cuuint64_t strides[3] = {(cuuint64_t)PF_D * es, (cuuint64_t)p.n_head * PF_D * es, (cuuint64_t)p.n_q * p.n_head * PF_D * es};
+        cuuint64_t dims[4] = {(cuuint64_t)Dr, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch};
+        cuuint64_t strides[3] = {(cuuint64_t)Dr * es, (cuuint64_t)p.n_head * Dr * es, (cuuint64_t)p.n_q * p.n_head * Dr * es};
         cuuint32_t box[4] = {(cuuint32_t)(64 / es), 1, 32, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&to, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.dst, dims, strides, box, estr,
@@ -352,7 +356,8 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     static const int poly = getenv("B200FA_POLY") ? atoi(getenv("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
     // two softmax threads per row: an experiment that measured HALF the speed of one thread per row (the per-half-tile
     // named barrier + shared-memory max exchange costs more than the extra warps hide); kept selectable for comparison
-    static const bool two = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "p2");
+    static const bool two_env = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "p2");
+    const bool two = two_env && Dr == PF_D;
     auto kern = two ? (poly == 0 ? fa_prefill_persistent2<0> : fa_prefill_persistent2<2>)
                     : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));
     static thread_local bool attr_set[64][6] = {};

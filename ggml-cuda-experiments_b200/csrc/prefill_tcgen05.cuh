@@ -671,7 +671,7 @@ inline PfDebug& pf_debug() {
 inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes, size_t cls_bytes, int sm_count,
                                   cudaStream_t st, int* launches) {
     (void)sm_count; (void)cls_bytes;
-    if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PF_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
+    if (p.D != PF_D || p.Dr != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PF_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
     int n = 0;
     const void* qbase = p.q;
     int64_t qnb1 = p.nb01, qnb2 = p.nb02, qnb3 = p.nb03;

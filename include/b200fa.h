@@ -76,7 +76,9 @@ int b200fa_version(void); /* major*10000 + minor*100 + patch */
  *   n_q * (n_head/n_head_kv) <= 64  -> split-KV register-streaming kernel, splits merged in-kernel (decode; HBM-bound)
  *   otherwise, D == 128, f16 K/V    -> tcgen05/TMEM/TMA tile kernel (prefill; tensor-bound)
  *   otherwise                       -> the register-streaming kernel over 16-row groups
- * Requirements: D in {64, 128}; rows of q/k/v 16-byte aligned for f16/f32 (nb % 16 == 0), 2-byte for q8_0.
+ * Requirements: head size D = ne00: any multiple of 8 up to 128 with f16 K/V (64 and 128 run natively; the others run
+ * zero-padded on the fly on the 64/128-wide kernels, nothing is copied), 64 or 128 with q8_0 K/V and in the partial /
+ * sequence-parallel entries; rows of q/k/v 16-byte aligned for f16/f32 (nb % 16 == 0), 2-byte for q8_0.
  */
 int b200fa_flash_attn_ext(
     const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
