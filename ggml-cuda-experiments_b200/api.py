@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
         l.b200fa_version.restype = C.c_int
         l.b200fa_flash_attn_ext.restype = C.c_int
         l.b200fa_flash_attn_ext.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 3 + [i64] * 23 + [C.c_uint32, vp, C.c_size_t, vp]
+        l.b200fa_flash_attn_ext2.restype = C.c_int
+        l.b200fa_flash_attn_ext2.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 3 + [i64] * 23 + [vp, C.c_uint32, vp, C.c_size_t, vp]
         l.b200fa_flash_attn_partial.restype = C.c_int
         l.b200fa_flash_attn_partial.argtypes = [vp] * 5 + [C.c_float] + [C.c_int] * 2 + [i64] * 21 + [C.c_uint32, vp, C.c_size_t, vp]
         l.b200fa_workspace_size.restype = C.c_size_t
@@ -122,9 +124,20 @@ class Workspace:
         self.ptr = (self.buf.data_ptr() + 255) // 256 * 256
 
 
+class ExtParams(C.Structure):
+    """b200fa_ext_params: the upstream-ggml score modifiers of b200fa_flash_attn_ext2."""
+    _fields_ = [("max_bias", C.c_float), ("logit_softcap", C.c_float)]
+
+
 def flash_attn_ext_raw(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb,
-                       flags, ws_ptr, ws_bytes, stream_ptr) -> int:
+                       flags, ws_ptr, ws_bytes, stream_ptr, max_bias: float = 0.0, logit_softcap: float = 0.0) -> int:
     """The ABI call.  q,k,v,mask,dst are device addresses (ints); returns the status code."""
+    if max_bias != 0.0 or logit_softcap != 0.0:
+        ext = ExtParams(max_bias, logit_softcap)
+        return lib().b200fa_flash_attn_ext2(
+            q, k, v, mask, dst, scale, q_type, kv_type, dst_type, *q_ne, *k_ne, ne31, nb31,
+            q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3],
+            q_ne[0], q_ne[2], q_ne[1], q_ne[3], C.byref(ext), flags, ws_ptr, ws_bytes, stream_ptr)
     return lib().b200fa_flash_attn_ext(
         q, k, v, mask, dst, scale, q_type, kv_type, dst_type, *q_ne, *k_ne, ne31, nb31,
         q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3],
@@ -132,8 +145,9 @@ def flash_attn_ext_raw(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, q_n
 
 
 def flash_attn_ext(q, k, v, mask=None, scale=None, dst=None, dst_dtype=None, flags=0, workspace: Workspace | None = None,
-                   stream=None, kv_type=None):
+                   stream=None, kv_type=None, max_bias: float = 0.0, logit_softcap: float = 0.0):
     """dst[b][q][head][D] = softmax(scale·QKᵀ + mask)·V on the current CUDA device.
+    max_bias / logit_softcap != 0 select b200fa_flash_attn_ext2 (ALiBi slopes on the mask, tanh soft-cap of the scores).
 
     q  : [n_batch][n_head][n_q][D] view (any strides with 16-byte aligned rows), f32 or f16
     k,v: [n_batch_kv][n_head_kv][n_kv][D] f16 views, or uint8 [..][n_kv][D/32*34] for q8_0
@@ -155,7 +169,7 @@ def flash_attn_ext(q, k, v, mask=None, scale=None, dst=None, dst_dtype=None, fla
     m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
     rc = flash_attn_ext_raw(q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, dt,
                             q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb, flags, workspace.ptr, workspace.nbytes,
-                            _stream_ptr(stream))
+                            _stream_ptr(stream), max_bias, logit_softcap)
     if rc != 0:
         raise B200FAError(rc, "b200fa_flash_attn_ext")
     return dst

@@ -78,6 +78,7 @@ struct Shape {
     const void* k; const void* v;
     int64_t kv_pos0, n_kv_total;
     int64_t Dr = 0;  // real head size when it differs from the structural D (0 = same)
+    bool ext = false;  // ALiBi / soft-cap requested (ext2 entry): only the persistent prefill kernel implements them
 };
 
 bool stream_eligible(const Shape& sh, bool sizing) {
@@ -99,7 +100,7 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     const int64_t gqa = n_head / n_head_kv;
     const int64_t rows = n_q * gqa;
     if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D <= 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64 &&
-        n_kv <= (sh.Dr == 0 || sh.Dr == 128 ? (int64_t)PF_MAX_KV_TILES * PF_BN : (int64_t)PP_MAX_KV_TILES * PF_BN)) {
+        n_kv <= ((sh.Dr == 0 || sh.Dr == 128) && !sh.ext ? (int64_t)PF_MAX_KV_TILES * PF_BN : (int64_t)PP_MAX_KV_TILES * PF_BN)) {
         pl.kind = kPrefill;
         if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * 128 * 2), 256);
         const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;
@@ -224,7 +225,7 @@ int validate(const void* q, const void* k, const void* v, const void* out, int q
     return B200FA_OK;
 }
 
-template <int D, int RH>
+template <int D, int RH, bool EXT>
 int launch_rows16(const FaParams& p, int n_groups, cudaStream_t st) {
     dim3 grid(p.n_splits, n_groups, p.n_head_kv * p.n_batch), block(kDecodeWarps * 32);
     constexpr int smem = FifoGeom<D>::kCtaBytes;  // cp.async FIFO (f16) / merge buffers (both)
@@ -233,26 +234,29 @@ int launch_rows16(const FaParams& p, int n_groups, cudaStream_t st) {
     cudaGetDevice(&dev);
     const int ti = p.kv_type == B200FA_TYPE_F16 ? 0 : 1;
     if (dev >= 0 && dev < 64 && !attr_set[dev][ti]) {
-        cudaError_t e = ti == 0 ? cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                : cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = ti == 0 ? cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, true, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                : cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH, true, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev][ti] = true;
     }
     static const int pipe = getenv("B200FA_DECODE_PIPE") ? atoi(getenv("B200FA_DECODE_PIPE")) : 1;
     if (ti == 0 && pipe == 0) {
         static thread_local bool a2[64] = {};
-        if (!a2[dev]) { cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a2[dev] = true; }
-        fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false><<<grid, block, smem, st>>>(p);
-    } else if (ti == 0) fa_rows16_splitkv<D, B200FA_TYPE_F16, RH><<<grid, block, smem, st>>>(p);
-    else fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH><<<grid, block, smem, st>>>(p);
+        if (!a2[dev]) { cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a2[dev] = true; }
+        fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false, EXT><<<grid, block, smem, st>>>(p);
+    } else if (ti == 0) fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, true, EXT><<<grid, block, smem, st>>>(p);
+    else fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH, true, EXT><<<grid, block, smem, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int run_rows16(FaParams& p, const Plan& pl, cudaStream_t st) {
     const bool small = (int64_t)p.n_q * p.gqa <= 8;  // one group of at most 8 rows: only fragment rows g are live
     int rc;
-    if (p.D == 128) rc = small ? launch_rows16<128, 1>(p, pl.n_groups, st) : launch_rows16<128, 2>(p, pl.n_groups, st);
-    else rc = small ? launch_rows16<64, 1>(p, pl.n_groups, st) : launch_rows16<64, 2>(p, pl.n_groups, st);
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
+#define B200FA_ROWS16(DD, RR) (ext ? launch_rows16<DD, RR, true>(p, pl.n_groups, st) : launch_rows16<DD, RR, false>(p, pl.n_groups, st))
+    if (p.D == 128) rc = small ? B200FA_ROWS16(128, 1) : B200FA_ROWS16(128, 2);
+    else rc = small ? B200FA_ROWS16(64, 1) : B200FA_ROWS16(64, 2);
+#undef B200FA_ROWS16
     g_last_launches++;
     return rc;
 }
@@ -263,14 +267,14 @@ int launch_combine(const float* part, int n_parts, int64_t rows, void* dst, int 
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
-template <int D, int KV, int RH>
+template <int D, int KV, int RH, bool EXT>
 int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t st) {
     constexpr int smem = dk_smem_bytes<D, KV == B200FA_TYPE_Q8_0, RH>();
     static thread_local bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
+        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev] = true;
     }
     if (a.cluster_k > 1) {
@@ -280,9 +284,9 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = a.cluster_k; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+        return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
     }
-    fa_decode_stream<D, KV, RH><<<grid, DK_THREADS, smem, st>>>(p, a, tk, tv);
+    fa_decode_stream<D, KV, RH, EXT><<<grid, DK_THREADS, smem, st>>>(p, a, tk, tv);
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
@@ -304,10 +308,13 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     static const int force_rh = getenv("B200FA_STREAM_RH") ? atoi(getenv("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
     const bool small = (int64_t)p.n_q * p.gqa <= 8 && force_rh != 2;
     g_last_launches++;
-#define B200FA_STREAM(DD, KK) (small ? launch_stream_t<DD, KK, 1>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2>(p, a, pl.grid, tk, tv, st))
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
+#define B200FA_STREAM_E(DD, KK, EE) (small ? launch_stream_t<DD, KK, 1, EE>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2, EE>(p, a, pl.grid, tk, tv, st))
+#define B200FA_STREAM(DD, KK) (ext ? B200FA_STREAM_E(DD, KK, true) : B200FA_STREAM_E(DD, KK, false))
     if (p.D == 128) return q8 ? B200FA_STREAM(128, B200FA_TYPE_Q8_0) : B200FA_STREAM(128, B200FA_TYPE_F16);
     return q8 ? B200FA_STREAM(64, B200FA_TYPE_Q8_0) : B200FA_STREAM(64, B200FA_TYPE_F16);
 #undef B200FA_STREAM
+#undef B200FA_STREAM_E
 }
 
 }  // namespace
@@ -367,7 +374,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
                        int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
                        int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
                        int64_t kv_pos0, int64_t n_kv_total, uint32_t flags, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st) {
+                       cudaStream_t st, const b200fa_ext_params* ext = nullptr) {
     g_last_dispatch = "none";
     g_last_launches = 0;
     const bool want_partial = partial_out != nullptr;
@@ -379,7 +386,10 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
 
     if (!(scale > 0.f)) flags |= B200FA_FLAG_NO_TCGEN05;  // the tile kernel takes row maxima of raw scores
     const int64_t Dp = ne00 <= 64 ? 64 : 128;  // structural head size of the decode kernels; the prefill kernel is always 128 wide
+    const float max_bias = ext ? ext->max_bias : 0.f, softcap = ext ? ext->logit_softcap : 0.f;
+    if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
     Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00};
+    sh.ext = max_bias > 0.f || softcap != 0.f;
     Plan pl = make_plan(sh, flags, di.sm_count, want_partial, false);
     if (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256)) return B200FA_ERR_WORKSPACE;
     char* ws = (char*)workspace;
@@ -401,6 +411,19 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.causal_off = n_kv_total - ne01;
     p.total_rows = ne03 * ne01 * ne02;
     { static const int dm = getenv("B200FA_DBG_MODE") ? atoi(getenv("B200FA_DBG_MODE")) : 0; p.dbg_mode = dm; }
+    if (max_bias > 0.f) {  // ALiBi slopes (upstream ggml: m0 = 2^(-max_bias/n_head_log2), m1 = 2^(-(max_bias/2)/n_head_log2))
+        int nhl2 = 1;
+        while (nhl2 * 2 <= (int)ne02) nhl2 *= 2;
+        p.alibi_nhl2 = nhl2;
+        p.alibi_m0l = -max_bias / (float)nhl2;
+        p.alibi_m1l = -(max_bias * 0.5f) / (float)nhl2;
+    }
+    if (softcap != 0.f) {  // s = cap * tanh(q.k * scale / cap)
+        const float cap = fabsf(softcap);  // the expression is even in cap
+        p.cap_in = scale / cap;
+        p.cap_out = cap * kLog2e;
+        p.cap_raw = cap / scale;
+    }
 
     if (pl.kind == kPrefill) {
         g_last_dispatch = "prefill_tcgen05";
@@ -446,6 +469,20 @@ int b200fa_flash_attn_ext(const void* q, const void* k, const void* v, const voi
     return attn_common(q, k, v, mask, dst, nullptr, scale, q_type, kv_type, dst_type, ne00, ne01, ne02, ne03, ne10, ne11,
                        ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, 0, ne11, flags,
                        workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200fa_flash_attn_ext2(const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+                           int q_type, int kv_type, int dst_type,
+                           int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                           int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                           int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                           int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                           int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3, const b200fa_ext_params* ext,
+                           uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    if (ne0 != ne00 || ne1 != ne02 || ne2 != ne01 || ne3 != ne03) return B200FA_ERR_INVALID;
+    return attn_common(q, k, v, mask, dst, nullptr, scale, q_type, kv_type, dst_type, ne00, ne01, ne02, ne03, ne10, ne11,
+                       ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, 0, ne11, flags,
+                       workspace, workspace_bytes, (cudaStream_t)stream, ext);
 }
 
 int b200fa_flash_attn_partial(const void* q, const void* k, const void* v, const void* mask, float* partial, float scale,

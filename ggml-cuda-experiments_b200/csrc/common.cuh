@@ -43,12 +43,32 @@ struct FaParams {
     int split_len;       // keys per split (multiple of 16)
     int64_t total_rows;  // n_batch * n_q * n_head
     int dbg_mode;        // tuning only (env B200FA_DBG_MODE): 1 = stream K/V but skip the tile maths
+    // b200fa_flash_attn_ext2 extensions (upstream ggml semantics; all zero / off on the reference's entry)
+    float alibi_m0l, alibi_m1l;  // log2 of the ALiBi bases: slope(h) = 2^(m0l*(h+1)) for h < n_head_log2, else 2^(m1l*(2(h-n_head_log2)+1))
+    int alibi_nhl2;              // n_head_log2; 0 = no ALiBi (slope 1)
+    float cap_in;                // logit soft-cap: s_log2 = tanh(qk * cap_in) * cap_out; cap_in = scale / cap; 0 = off
+    float cap_out;               //                 cap * log2(e)
+    float cap_raw;               // cap / scale: tanh(qk * cap_in) * cap_raw is the capped score in RAW (unscaled) units
 };
+
+// ALiBi slope of query head h (1 when off)
+__device__ __forceinline__ float fa_slope(const FaParams& p, int h) {
+    if (p.alibi_nhl2 == 0) return 1.f;
+    return exp2f(h < p.alibi_nhl2 ? p.alibi_m0l * (float)(h + 1) : p.alibi_m1l * (float)(2 * (h - p.alibi_nhl2) + 1));
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// tanh through ex2 + rcp (tanh.approx is only good to 2^-11, which a soft-cap of 30-50 would turn into visible score errors)
+__device__ __forceinline__ float fa_tanh(float x) {
+    const float e = fast_exp2(x * 2.88539008f);  // e^(2x); inf for large x -> 1, 0 for very negative x -> -1
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
 }
 
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {

@@ -123,7 +123,7 @@ struct KVTile {
 };
 
 // RH = 1: the group has at most 8 live rows (only fragment rows g), RH = 2: up to 16 (rows g and g+8)
-template <int D, int KV_TYPE, int RH, bool FIFO = true>
+template <int D, int KV_TYPE, int RH, bool FIFO = true, bool EXT = false>
 __global__ void __launch_bounds__(kDecodeWarps * 32, 2)
 fa_rows16_splitkv(const __grid_constant__ FaParams p) {
     static_assert(D == 64 || D == 128, "head size");
@@ -152,6 +152,10 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
         iq1r[h] = Rc / p.gqa;
         iq2r[h] = ik2 * p.gqa + Rc % p.gqa;
     }
+
+    float mslope[RH];  // log2(e) x ALiBi slope of the row's head: the factor on raw mask values
+#pragma unroll
+    for (int h = 0; h < RH; h++) mslope[h] = EXT ? kLog2e * fa_slope(p, iq2r[h]) : kLog2e;
 
     // ---- Q fragments (f16; an f32 Q is rounded like the reference does, flash-llama.h:80) ----
     uint32_t qa[NC4][RH][4];
@@ -454,12 +458,16 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
             if (p.mask != nullptr) {
                 const float2 m01 = __half22float2(*reinterpret_cast<const __half2*>(&T.mk[h].x));
                 const float2 m23 = __half22float2(*reinterpret_cast<const __half2*>(&T.mk[h].y));
-                mv[0] = m01.x * kLog2e; mv[1] = m01.y * kLog2e; mv[2] = m23.x * kLog2e; mv[3] = m23.y * kLog2e;
+                const float ms = EXT ? mslope[h] : kLog2e;
+                mv[0] = m01.x * ms; mv[1] = m01.y * ms; mv[2] = m23.x * ms; mv[3] = m23.y * ms;
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int kv = kv0 + 4 * t + j;
-                float x = fmaf(s[j >> 1][2 * h + (j & 1)], p.scale_log2, mv[j]);
+                const float sv = s[j >> 1][2 * h + (j & 1)];
+                float x;
+                if (EXT && p.cap_in != 0.f) x = fmaf(fa_tanh(sv * p.cap_in), p.cap_out, mv[j]);
+                else x = fmaf(sv, p.scale_log2, mv[j]);
                 if (kv >= lim[h]) x = -INFINITY;
                 pr[h][j] = x;
                 tmax = fmaxf(tmax, x);

@@ -133,7 +133,8 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) { asm vol
 // owner CTA of flat chunk x when CTA c covers [c*T/G, (c+1)*T/G)
 __device__ __forceinline__ long long dk_owner(long long x, long long T, long long G) { return ((x + 1) * G - 1) / T; }
 
-template <int D, int KV_TYPE, int RH>
+// EXT: the ext2 score modifiers (ALiBi slope on the mask, tanh soft-cap) are compiled in; the plain entry never pays for them
+template <int D, int KV_TYPE, int RH, bool EXT = false>
 __global__ void __launch_bounds__(DK_THREADS, 1)
 fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkArgs a,
                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV) {
@@ -230,6 +231,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     float m_run[RH], l_run[RH];
     uint32_t qa[NC4][RH][4];
     int iq1r[RH], rq[RH];   // query position / q head within the GQA group of the lane's rows
+    float mslope[RH];       // log2(e) x ALiBi slope of the row's head (set per unit): the factor on raw mask values
     bool rvalid[RH];
     int lim[RH];
     const char* mrow[RH];
@@ -242,6 +244,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const int64_t vis = p.causal ? (int64_t)iq1r[h] + p.causal_off - p.kv_pos0 + 1 : (int64_t)p.n_kv;
         lim[h] = (int)max((int64_t)0, min((int64_t)a.kv_end, vis));
         mrow[h] = p.mask ? p.mask + (int64_t)iq1r[h] * p.nb31 : nullptr;
+        mslope[h] = kLog2e;
     }
 
     // S = Q K^T (fp32) for the lane's 2 x 4 score slots
@@ -285,12 +288,16 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             if (p.mask != nullptr) {
                 const float2 m01 = __half22float2(*reinterpret_cast<const __half2*>(&T.mk[h].x));
                 const float2 m23 = __half22float2(*reinterpret_cast<const __half2*>(&T.mk[h].y));
-                mv[0] = m01.x * kLog2e; mv[1] = m01.y * kLog2e; mv[2] = m23.x * kLog2e; mv[3] = m23.y * kLog2e;
+                const float ms = EXT ? mslope[h] : kLog2e;
+                mv[0] = m01.x * ms; mv[1] = m01.y * ms; mv[2] = m23.x * ms; mv[3] = m23.y * ms;
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int kv = kv0 + 4 * t + j;
-                float x = fmaf(s[j >> 1][2 * h + (j & 1)], p.scale_log2, mv[j]);
+                const float sv = s[j >> 1][2 * h + (j & 1)];
+                float x;
+                if (EXT && p.cap_in != 0.f) x = fmaf(fa_tanh(sv * p.cap_in), p.cap_out, mv[j]);
+                else x = fmaf(sv, p.scale_log2, mv[j]);
                 if (kv >= lim[h]) x = -INFINITY;
                 pr[h][j] = x;
                 tmax = fmaxf(tmax, x);
@@ -530,6 +537,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         // ---- Q fragments of this unit's rows (f16; an f32 Q is rounded like the reference does, flash-llama.h:80) ----
 #pragma unroll
         for (int h = 0; h < RH; h++) {
+            if constexpr (EXT) mslope[h] = kLog2e * fa_slope(p, ik2 * p.gqa + rq[h]);
             const char* qrow = p.q + (int64_t)iq1r[h] * p.nb01 + (int64_t)(ik2 * p.gqa + rq[h]) * p.nb02 + (int64_t)iq3 * p.nb03;
 #pragma unroll
             for (int c = 0; c < NC4; c++) {

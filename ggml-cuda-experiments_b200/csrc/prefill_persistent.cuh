@@ -221,7 +221,7 @@ __device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& 
     }
 }
 
-template <int POLY>
+template <int POLY, bool EXT = false>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant__ PpArgs pa,
                       const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -301,6 +301,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             const char* mrow = (p.mask != nullptr && !causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
             const int64_t vis = causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
             float m_ref = -INFINITY, l = 0.f;
+            const float mask_mul = EXT ? a.inv_scale * fa_slope(p, iq2) : a.inv_scale;  // mask values are folded into RAW scores: x slope / scale
             int g = 0;  // half tiles of this item done
             for (int j = j_lo; j < j_hi; j++) {
                 const int cls = (sm.cls2[slot][j] >> (2 * t)) & 3;
@@ -315,6 +316,12 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                     tmem_ld32(tSh, s[0]);
                     tmem_ld32(tSh + 32u, s[1]);
                     tmem_wait_ld();
+                    if (EXT && p.cap_in != 0.f) {  // logit soft-cap (ext2): s <- cap*tanh(s*scale/cap), kept in raw units (divided by scale)
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; q2++)
+#pragma unroll
+                            for (int i = 0; i < 32; i++) s[q2][i] = __float_as_uint(fa_tanh(__uint_as_float(s[q2][i]) * p.cap_in) * p.cap_raw);
+                    }
                     if (cls == 1) {
                         const int kv0 = j * PF_BN + 64 * h;
                         const int lim = (int)min((int64_t)(p.n_kv - 1), vis) - kv0;  // last visible column of this half for this row
@@ -329,15 +336,15 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
 #pragma unroll
                                         for (int e = 0; e < 4; e++) {
                                             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wd[e]));
-                                            s[q2][v8 * 8 + 2 * e] = __float_as_uint(__uint_as_float(s[q2][v8 * 8 + 2 * e]) + f.x * a.inv_scale);
-                                            s[q2][v8 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(s[q2][v8 * 8 + 2 * e + 1]) + f.y * a.inv_scale);
+                                            s[q2][v8 * 8 + 2 * e] = __float_as_uint(__uint_as_float(s[q2][v8 * 8 + 2 * e]) + f.x * mask_mul);
+                                            s[q2][v8 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(s[q2][v8 * 8 + 2 * e + 1]) + f.y * mask_mul);
                                         }
                                     }
                                 } else {
 #pragma unroll
                                     for (int i = 0; i < 32; i++) {
                                         const int kv = kv0 + q2 * 32 + i;
-                                        if (kv < p.n_kv) s[q2][i] = __float_as_uint(__uint_as_float(s[q2][i]) + ld_mask(mrow, kv) * a.inv_scale);
+                                        if (kv < p.n_kv) s[q2][i] = __float_as_uint(__uint_as_float(s[q2][i]) + ld_mask(mrow, kv) * mask_mul);
                                     }
                                 }
                             }

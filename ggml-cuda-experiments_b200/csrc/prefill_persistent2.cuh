@@ -357,13 +357,15 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     // two softmax threads per row: an experiment that measured HALF the speed of one thread per row (the per-half-tile
     // named barrier + shared-memory max exchange costs more than the extra warps hide); kept selectable for comparison
     static const bool two_env = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "p2");
-    const bool two = two_env && Dr == PF_D;
-    auto kern = two ? (poly == 0 ? fa_prefill_persistent2<0> : fa_prefill_persistent2<2>)
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;  // ext2 score modifiers: their own instantiation
+    const bool two = two_env && Dr == PF_D && !ext;
+    auto kern = ext ? fa_prefill_persistent<2, true>
+              : two ? (poly == 0 ? fa_prefill_persistent2<0> : fa_prefill_persistent2<2>)
                     : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));
-    static thread_local bool attr_set[64][6] = {};
+    static thread_local bool attr_set[64][7] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int ai = two ? (poly == 0 ? 4 : 5) : (poly == 0 ? 0 : (poly == 3 ? 2 : (poly == 4 ? 3 : 1)));
+    const int ai = ext ? 6 : two ? (poly == 0 ? 4 : 5) : (poly == 0 ? 0 : (poly == 3 ? 2 : (poly == 4 ? 3 : 1)));
     if (dev >= 0 && dev < 64 && !attr_set[dev][ai]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
             return B200FA_ERR_CUDA;

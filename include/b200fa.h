@@ -92,6 +92,31 @@ int b200fa_flash_attn_ext(
     int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
     uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
 
+/*
+ * The same call with the two score modifiers of upstream ggml's flash_attn_ext (NOT in the reference,
+ * whose kernel has neither — semantics restated from ggml, parity unpinned by the reference):
+ *     s = q.k * scale;   if (logit_softcap != 0) s = logit_softcap * tanh(s / logit_softcap);   s += slope(head) * mask
+ *     slope(h) = 1 when max_bias == 0, else ALiBi: n2 = 2^floor(log2(n_head)), m0 = 2^(-max_bias/n2), m1 = 2^(-max_bias/2/n2),
+ *                h < n2 ? m0^(h+1) : m1^(2(h-n2)+1)
+ * ext == NULL or {0, 0} is exactly b200fa_flash_attn_ext.  B200FA_FLAG_CAUSAL still means "the mask is exactly 0 / -inf causal".
+ */
+typedef struct b200fa_ext_params {
+    float max_bias;       /* >= 0; 0 = no ALiBi */
+    float logit_softcap;  /* 0 = off */
+} b200fa_ext_params;
+int b200fa_flash_attn_ext2(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+    const b200fa_ext_params* ext,
+    uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
+
 /* Bytes of workspace b200fa_flash_attn_ext needs for this shape on the current device
  * (split-KV partials, an f16 copy of an f32 Q for the tcgen05 path, mask tile classes).
  * Replaces the inline cudaMalloc of flash-matrix.cu:223-224 / kernel_test.h:153-155. */

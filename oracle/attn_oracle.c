@@ -143,6 +143,7 @@ typedef struct {
     int64_t nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23;
     int64_t ne0, ne1, ne2, ne3;
     int round_q_f16, strict_ref;
+    float max_bias, logit_softcap; /* upstream ggml_flash_attn_ext extensions (0 = off); see oracle_flash_attn_ext2 */
 } oracle_args;
 
 /* widen one K/V row (ne10 elements) to f32 */
@@ -175,13 +176,26 @@ static void attend_head(const oracle_args* a, int64_t iq3, int64_t iq2, float* s
             qrow[i] = x;
         }
         const uint16_t* mrow = a->mask ? (const uint16_t*)(a->mask + iq1 * a->nb31) : NULL; /* flash-llama.h:151 */
+        /* ALiBi slope of this head and logit soft-cap — upstream ggml semantics, NOT in the reference (see oracle_flash_attn_ext2) */
+        float slope = 1.0f;
+        if (a->max_bias > 0.0f) {
+            const uint32_t n_head_log2 = 1u << (uint32_t)floor(log2((double)a->ne02));
+            const float m0 = powf(2.0f, -(a->max_bias) / n_head_log2);
+            const float m1 = powf(2.0f, -(a->max_bias / 2.0f) / n_head_log2);
+            const uint32_t h = (uint32_t)iq2;
+            slope = h < n_head_log2 ? powf(m0, (float)(h + 1)) : powf(m1, (float)(2 * (h - n_head_log2) + 1));
+        }
+        const float cap = a->logit_softcap;
+        const float qk_scale = cap != 0.0f ? a->scale / cap : a->scale;
 
         /* scores = scale * q·k + mask   (utils.h:18-28: acc over k, then acc*scale + mask) */
         for (int64_t ic = 0; ic < n_kv; ic++) {
             load_kv_row(a->k + ic * a->nb11 + ik2 * a->nb12 + ik3 * a->nb13, a->kv_type, D, kvrow);
             float s = 0.0f;
             for (int64_t i = 0; i < D; i++) s += qrow[i] * kvrow[i];
-            scores[ic] = s * a->scale + (mrow ? h2f(mrow[ic]) : 0.0f);
+            s *= qk_scale;
+            if (cap != 0.0f) s = cap * tanhf(s);
+            scores[ic] = s + (mrow ? slope * h2f(mrow[ic]) : 0.0f);
         }
 
         /* softmax (utils.h:30-49): online (M,S), then expf(s-M)/S */
@@ -236,7 +250,28 @@ static void* worker(void* p) {
 }
 
 /* Same argument list as the C-ABI entry (include/b200fa.h), minus flags/workspace/stream, plus the
- * two oracle switches and a thread count.  Returns 0, or -1 on an argument it cannot interpret. */
+ * two oracle switches and a thread count.  Returns 0, or -1 on an argument it cannot interpret.
+ *
+ * max_bias / logit_softcap (b200fa_flash_attn_ext2) are NOT in the reference: PARITY UNPINNED for them.
+ * They restate the published semantics of upstream ggml's ggml_flash_attn_ext (ggml.c, flash_attn_ext_f16 forward, not vendored):
+ *     n_head_log2 = 2^floor(log2(n_head));  m0 = 2^(-max_bias/n_head_log2);  m1 = 2^(-(max_bias/2)/n_head_log2)
+ *     slope(h)    = max_bias > 0 ? (h < n_head_log2 ? m0^(h+1) : m1^(2(h-n_head_log2)+1)) : 1
+ *     s           = q.k * scale            (scale /= softcap first when softcap != 0)
+ *     s           = softcap * tanhf(s)     (when softcap != 0)
+ *     s          += slope(h) * mask[q][k]
+ */
+int oracle_flash_attn_ext2(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+    int round_q_f16, int strict_ref, int nthreads, float max_bias, float logit_softcap);
+
 int oracle_flash_attn_ext(
     const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
     int q_type, int kv_type, int dst_type,
@@ -249,6 +284,23 @@ int oracle_flash_attn_ext(
     int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
     int round_q_f16, int strict_ref, int nthreads)
 {
+    return oracle_flash_attn_ext2(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13,
+                                  ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, ne0, ne1, ne2, ne3,
+                                  round_q_f16, strict_ref, nthreads, 0.0f, 0.0f);
+}
+
+int oracle_flash_attn_ext2(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+    int round_q_f16, int strict_ref, int nthreads, float max_bias, float logit_softcap)
+{
     if (!q || !k || !v || !dst) return -1;
     if (ne00 != ne10 || ne00 <= 0 || ne12 <= 0 || ne13 <= 0) return -1;
     if (ne02 % ne12 || ne03 % ne13) return -1;
@@ -259,7 +311,7 @@ int oracle_flash_attn_ext(
         q_type, kv_type, dst_type,
         ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13, ne31, nb31,
         nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23,
-        ne0, ne1, ne2, ne3, round_q_f16, strict_ref };
+        ne0, ne1, ne2, ne3, round_q_f16, strict_ref, max_bias, logit_softcap };
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if (nthreads == 1) {
