@@ -299,12 +299,24 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     a.cluster_k = pl.cluster_k;
     a.peers = g_seqpar.peers; a.rank = g_seqpar.rank; a.world = g_seqpar.world; a.fdst = g_seqpar.fdst; a.fdst_type = g_seqpar.fdst_type;
     a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
+    { static const bool nb = getenv("B200FA_NO_MASK_BULK") != nullptr; if (nb) a.mask_bulk = 0; }
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {
         if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
         if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
     }
     const bool q8 = p.kv_type == B200FA_TYPE_Q8_0;
+    if (q8) {
+        // the contiguous rows of a head as a [lines][128 B] byte tensor (whole lines only: nothing past the head is ever read)
+        static const bool no_lines = getenv("B200FA_Q8_BULK1D") != nullptr;
+        const int64_t lines = (int64_t)p.n_kv * (p.D / kQ8BlockElems * kQ8BlockBytes) / 128;
+        if (!no_lines && lines > 0) {
+            const int box_lines = DK_CHUNK * (p.D / kQ8BlockElems * kQ8BlockBytes) / 128;
+            if (!make_line_map(&tk, p.k, lines, p.n_head_kv, p.n_batch_kv, p.nb12, p.nb13, box_lines)) return B200FA_ERR_CUDA;
+            if (!make_line_map(&tv, p.v, lines, p.n_head_kv, p.n_batch_kv, p.nb22, p.nb23, box_lines)) return B200FA_ERR_CUDA;
+            a.q8_lines = (int)(lines > 0x7fffffff ? 0x7fffffff : lines);
+        }
+    }
     static const int force_rh = getenv("B200FA_STREAM_RH") ? atoi(getenv("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
     const bool small = (int64_t)p.n_q * p.gqa <= 8 && force_rh != 2;
     g_last_launches++;

@@ -34,7 +34,8 @@ namespace b200fa {
 
 constexpr int DK_CHUNK = 64;   // keys per pipeline stage
 constexpr int DK_CWARPS = 8;   // consumer warps (two groups of four)
-constexpr int DK_THREADS = (DK_CWARPS + 1) * 32;
+constexpr int DK_PWARPS = 2;   // producer warps: one issues the K operations of a chunk, the other V and the mask rows
+constexpr int DK_THREADS = (DK_CWARPS + DK_PWARPS) * 32;
 constexpr int DK_SLOTS = DK_CWARPS;  // cross-warp merge slots: one per consumer warp
 constexpr int DK_MASK_BYTES = 16 * 128;
 constexpr int DK_REC_ROWS = 16;
@@ -55,6 +56,7 @@ struct DkMerge {
     static constexpr int kSlotBytes = kFloatsPerLane * 32 * 4;
     static constexpr int kBytes = DK_SLOTS * kSlotBytes;
 };
+constexpr int DK_TL_CHUNK0 = 160 * 8;  // diagnostics: per-chunk stamps of CTA 0 start here (4 per chunk, first 512 chunks)
 constexpr int DK_TAB = 160;           // contributor table entries (>= SM count)
 constexpr int DK_TAIL_BYTES = 2 * 8 * 8 + 64 + DK_TAB * 4;  // barriers, flag, table
 constexpr int DK_SMEM_LIMIT = 227 * 1024;
@@ -88,6 +90,7 @@ struct DkArgs {
     int rank, world;
     void* fdst;              // final merged output [rows][D]
     int fdst_type;
+    int q8_lines;            // q8_0: whole 128-byte lines per head covered by the [lines][128 B] tensor maps (0 = 1-D bulk copies only)
     int cluster_k;           // > 1: the grid is launched in clusters of cluster_k CTAs = the CTAs of one unit; their records are
                              // merged through distributed shared memory (no global fence / atomic / L2 round trips)
 };
@@ -165,13 +168,19 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     const long long start = (long long)blockIdx.x * a.total / G, stop = ((long long)blockIdx.x + 1) * a.total / G;
     const int my_chunks = (int)(stop - start);
 
-    if (warp == DK_CWARPS) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    if (warp >= DK_CWARPS) {
+        // ===================== producers =====================
+        // Every TMA / bulk operation costs its issuing thread ~90 ns (measured: +10 us on the C5 shape for one extra 128-byte copy
+        // per chunk), and a q8_0 chunk is only 17 KB: a single issuer was the bottleneck of the q8_0 stream (period 690 ns per
+        // chunk, 510 of them spent issuing).  Two warps issue side by side: warp 8 the K operations, warp 9 V and the mask rows;
+        // each arms the chunk's barrier with its own byte count.  (Lanes of ONE warp issuing side by side measured slower.)
+        const int which = warp - DK_CWARPS;
+        if (which == 0 && lane == 0) {
+            for (int s = 0; s < NS; s++) { mbar_init(&full[s], DK_PWARPS); mbar_init(&empty[s], 4); }
             fence_barrier_init();
-            if constexpr (!Q8) { prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); }
         }
+        if (lane == 0 && (!Q8 || a.q8_lines > 0)) prefetch_tensormap(which == 0 ? &tmK : &tmV);
+        asm volatile("bar.sync 2, %0;" ::"n"(DK_PWARPS * 32) : "memory");  // the barriers exist before the other producer touches them
         int pu = (int)(start / a.cph), pch = (int)(start - (long long)pu * a.cph);  // unit / chunk of the next issue
         auto issue = [&](int i) {
             const int u = pu, ch = pch;
@@ -179,32 +188,35 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv, ik3 = iq3 / p.rk3;
             const int key0 = ch * DK_CHUNK;
             const int stage = i % NS;
-            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes;
+            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes + (which == 0 ? 0 : Geo::kVOff);  // this producer's half of the stage
+            uint8_t* sp = smem + stage * Geo::kStageBytes + (which == 0 ? 0 : Geo::kVOff);
             const bool whole = key0 + DK_CHUNK <= p.n_kv;
-            const int mrows = (a.mask_bulk && whole) ? p.n_q : 0;
+            const int mrows = (which == 1 && a.mask_bulk && whole) ? p.n_q : 0;
+            const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
             if constexpr (!Q8) {
-                mbar_arrive_expect_tx(&full[stage], 2 * Geo::kKBytes + mrows * 128);
+                mbar_arrive_expect_tx(&full[stage], Geo::kKBytes + mrows * 128);
 #pragma unroll
-                for (int b = 0; b < Geo::kBoxes; b++) {
-                    tma_load_4d(smem + stage * Geo::kStageBytes + b * 8192, &tmK, &full[stage], 64 * b, key0, ik2, ik3);
-                    tma_load_4d(smem + stage * Geo::kStageBytes + Geo::kVOff + b * 8192, &tmV, &full[stage], 64 * b, key0, ik2, ik3);
-                }
+                for (int b = 0; b < Geo::kBoxes; b++) tma_load_4d(sp + b * 8192, tm, &full[stage], 64 * b, key0, ik2, ik3);
+            } else if (a.q8_lines > 0 && (int64_t)(ch + 1) * Geo::kKBytes <= (int64_t)a.q8_lines * 128) {
+                // q8_0, chunk inside the whole-128-byte-line part of the head: the head's rows are one contiguous byte range, which
+                // the tensor maps describe as [lines][128 B] — one box of kKBytes/128 lines per K and per V chunk (a little faster
+                // than 1-D bulk copies of the same bytes: 71 vs 74-81 us of pure streaming on the C5 shape).
+                mbar_arrive_expect_tx(&full[stage], Geo::kKBytes + mrows * 128);
+                tma_load_4d(sp, tm, &full[stage], 0, ch * (Geo::kKBytes / 128), ik2, ik3);
             } else {
+                // ragged or unaligned tail of a q8_0 head: a 1-D bulk copy of the 16-byte multiple, the last few words by hand
                 const int rows = min(DK_CHUNK, p.n_kv - key0);
                 const uint32_t nbytes = (uint32_t)rows * Geo::kRowBytes, nb16 = nbytes & ~15u;
-                const char* ksrc = p.k + (int64_t)ik2 * p.nb12 + (int64_t)ik3 * p.nb13 + (int64_t)key0 * Geo::kRowBytes;
-                const char* vsrc = p.v + (int64_t)ik2 * p.nb22 + (int64_t)ik3 * p.nb23 + (int64_t)key0 * Geo::kRowBytes;
-                for (uint32_t o = nb16; o < nbytes; o += 4) {  // odd ragged tail: a few plain words
-                    *reinterpret_cast<uint32_t*>(smem + stage * Geo::kStageBytes + o) = __ldg(reinterpret_cast<const uint32_t*>(ksrc + o));
-                    *reinterpret_cast<uint32_t*>(smem + stage * Geo::kStageBytes + Geo::kVOff + o) = __ldg(reinterpret_cast<const uint32_t*>(vsrc + o));
-                }
-                mbar_arrive_expect_tx(&full[stage], 2 * nb16 + mrows * 128);
-                bulk_g2s(sb, ksrc, nb16, &full[stage]);
-                bulk_g2s(sb + Geo::kVOff, vsrc, nb16, &full[stage]);
+                const char* src = which == 0 ? p.k + (int64_t)ik2 * p.nb12 + (int64_t)ik3 * p.nb13 + (int64_t)key0 * Geo::kRowBytes
+                                             : p.v + (int64_t)ik2 * p.nb22 + (int64_t)ik3 * p.nb23 + (int64_t)key0 * Geo::kRowBytes;
+                for (uint32_t o = nb16; o < nbytes; o += 4) *reinterpret_cast<uint32_t*>(sp + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
+                mbar_arrive_expect_tx(&full[stage], nb16 + mrows * 128);
+                if (nb16 > 0) bulk_g2s(sb, src, nb16, &full[stage]);
             }
             for (int r = 0; r < mrows; r++)
-                bulk_g2s(sb + Geo::kMaskOff + r * 128, p.mask + (int64_t)r * p.nb31 + (int64_t)key0 * 2, 128, &full[stage]);
+                bulk_g2s(stages_u32 + stage * Geo::kStageBytes + Geo::kMaskOff + r * 128, p.mask + (int64_t)r * p.nb31 + (int64_t)key0 * 2, 128, &full[stage]);
         };
+        const bool tl = a.timeline != nullptr && blockIdx.x == 0 && which == 0;  // per-chunk diagnostics of CTA 0
         int i = 0;
         if (lane == 0)
             for (; i < min(NS, my_chunks); i++) issue(i);  // the ring starts filling before anyone else is ready
@@ -212,7 +224,9 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         if (lane == 0) {
             for (; i < my_chunks; i++) {
                 mbar_wait(&empty[i % NS], ((i / NS) & 1) ^ 1);
+                if (tl && i < 512) a.timeline[DK_TL_CHUNK0 + i * 4 + 0] = dk_now();  // stage free again
                 issue(i);
+                if (tl && i < 512) a.timeline[DK_TL_CHUNK0 + i * 4 + 1] = dk_now();  // operations issued
             }
         }
         __syncwarp();
@@ -227,7 +241,9 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     const int rows_total = p.n_q * p.gqa;
     const bool mask_al8 = p.mask != nullptr && ((((uintptr_t)p.mask | (uintptr_t)p.nb31) & 7) == 0);
 
-    float o[NT][2 * RH];
+    // Full accumulator quads also when only fragment rows g are live (RH == 1): rows 8-15 of A are fed zeros, so entries 2-3 stay
+    // what they were (zero) and the HMMA accumulates in place — no per-instruction re-zeroing or moves to build its C/D quad.
+    float o[NT][4];
     float m_run[RH], l_run[RH];
     uint32_t qa[NC4][RH][4];
     int iq1r[RH], rq[RH];   // query position / q head within the GQA group of the lane's rows
@@ -251,7 +267,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     auto qk_tile = [&](const Tile& T, float (&s)[2][4]) {
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            if constexpr (Q8) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
             for (int c = 0; c < NC4; c++) {
                 uint32_t k0, k1, k2, k3;
@@ -261,15 +277,13 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                     q8x4_to_h2(T.kf[nt][c][0], k0, k1);
                     q8x4_to_h2(T.kf[nt][c][1], k2, k3);
                 }
-                float acc0[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc0[4];
                 float(&acc)[4] = Q8 ? acc0 : s[nt];
-                if constexpr (RH == 2) {
-                    mma_16816(acc, qa[c][0][0], qa[c][1][0], qa[c][0][1], qa[c][1][1], k0, k1);
-                    mma_16816(acc, qa[c][0][2], qa[c][1][2], qa[c][0][3], qa[c][1][3], k2, k3);
-                } else {
-                    mma_16816_top(acc[0], acc[1], qa[c][0][0], qa[c][0][1], k0, k1);
-                    mma_16816_top(acc[0], acc[1], qa[c][0][2], qa[c][0][3], k2, k3);
-                }
+                const uint32_t q1a = RH == 2 ? qa[c][RH - 1][0] : 0u, q1b = RH == 2 ? qa[c][RH - 1][1] : 0u;
+                const uint32_t q1c = RH == 2 ? qa[c][RH - 1][2] : 0u, q1d = RH == 2 ? qa[c][RH - 1][3] : 0u;
+                if (Q8 || c == 0) mma_16816_zc(acc, qa[c][0][0], q1a, qa[c][0][1], q1b, k0, k1);  // fresh block sum / first block: C = 0
+                else mma_16816(acc, qa[c][0][0], q1a, qa[c][0][1], q1b, k0, k1);
+                mma_16816(acc, qa[c][0][2], q1c, qa[c][0][3], q1d, k2, k3);
                 if constexpr (Q8) {
                     const float d0 = h_bits_to_f(T.kd[2 * nt][c]), d1 = h_bits_to_f(T.kd[2 * nt + 1][c]);
                     s[nt][0] += acc0[0] * d0; s[nt][1] += acc0[1] * d1;
@@ -347,8 +361,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
                 const uint32_t b0 = prmt(vv[0][j >> 1], vv[1][j >> 1], sel);
                 const uint32_t b1 = prmt(vv[2][j >> 1], vv[3][j >> 1], sel);
-                if constexpr (RH == 2) mma_16816(o[c * 8 + j], pa0, pa1, pa2, pa3, b0, b1);
-                else mma_16816_top(o[c * 8 + j][0], o[c * 8 + j][1], pa0, pa2, b0, b1);
+                mma_16816(o[c * 8 + j], pa0, pa1, pa2, pa3, b0, b1);  // RH == 1: pa1 = pa3 = 0
             }
         }
     };
@@ -558,7 +571,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 #pragma unroll
         for (int n = 0; n < NT; n++)
 #pragma unroll
-            for (int e = 0; e < 2 * RH; e++) o[n][e] = 0.f;
+            for (int e = 0; e < 4; e++) o[n][e] = 0.f;
 #pragma unroll
         for (int h = 0; h < RH; h++) { m_run[h] = -INFINITY; l_run[h] = 0.f; }
 
@@ -570,9 +583,11 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             mbar_wait(&full[stage], (j / NS) & 1);
             __syncwarp();
             if (stamp && j == 0) a.timeline[blockIdx.x * 8 + 1] = dk_now();
+            const bool cstamp = a.timeline != nullptr && blockIdx.x == 0 && sub == 0 && lane == 0 && j < 512;  // per-chunk diagnostics of CTA 0
+            if (cstamp) a.timeline[DK_TL_CHUNK0 + j * 4 + 2] = dk_now();  // chunk landed (as seen by its first consumer warp)
             Tile T;
             float s[2][4];
-            const bool live = kv0 < a.kv_end;
+            const bool live = kv0 < a.kv_end && p.dbg_mode != 1;  // tuning aid (env B200FA_DBG_MODE=1): stream the chunks, touch nothing
             const uint32_t sb = stages_u32 + stage * Geo::kStageBytes;
             if (live) {
                 read_k(T, sb, kv0, a.mask_bulk && key0 + DK_CHUNK <= p.n_kv);
@@ -590,6 +605,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);  // fragments are in registers: hand the stage back
+            if (cstamp) a.timeline[DK_TL_CHUNK0 + j * 4 + 3] = dk_now();
             if (live) softmax_pv_tile(T, s, kv0);
         }
 

@@ -658,6 +658,20 @@ inline bool make_tile_map(CUtensorMap* m, const void* base, int64_t rows, int64_
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// byte tensor [128][lines][heads][batch] (a contiguous byte range per head seen as 128-byte lines); box = 128 x box_lines, no swizzle
+inline bool make_line_map(CUtensorMap* m, const void* base, int64_t lines, int64_t heads, int64_t batch, int64_t nb2, int64_t nb3,
+                          int box_lines) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {128, (cuuint64_t)lines, (cuuint64_t)heads, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {128, (cuuint64_t)nb2, (cuuint64_t)nb3};
+    cuuint32_t box[4] = {128, (cuuint32_t)box_lines, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct PfDebug {
     unsigned long long* dbg = nullptr;
     float* dump = nullptr;

@@ -26,7 +26,7 @@ if a.q8:
     k, v = P.quantize_q8_0(k), P.quantize_q8_0(v)
 q = torch.rand((a.batch, a.hq, 1, D), device=dev) * 2 - 1
 mask = torch.zeros((32, a.nkv), dtype=torch.float16, device=dev)
-stamps = torch.zeros((160, 8), dtype=torch.int64, device=dev)
+stamps = torch.zeros((160 + 256, 8), dtype=torch.int64, device=dev)  # 160 CTAs x 8, then 512 chunks x 4 of CTA 0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for it in range(3):
     flush.fill_(it)  # evict K/V from L2
@@ -35,7 +35,9 @@ for it in range(3):
     P.flash_attn_ext(q, k, v, mask)
     torch.cuda.synchronize()
     P.lib().b200fa_debug_timeline(None)
-    s = stamps.cpu().numpy()
+    s_all = stamps.cpu().numpy()
+    s = s_all[:160]
+    ch = s_all[160:].reshape(-1, 4)
     s = s[s[:, 0] > 0]
     t0 = s[:, 0].min()
     names = ["start", "first stage", "stream end", "fold done", "end"]
@@ -53,3 +55,12 @@ for it in range(3):
             sel = s[s[:, 5] == ns]
             if len(sel):
                 print(f"  CTAs with {ns} segment(s): {len(sel)}; stream_end median {int(np.median(sel[:, 2] - t0))}, end median {int(np.median(sel[:, 4] - t0))}")
+
+# per-chunk view of CTA 0 (ns): stage freed -> operations issued -> landed -> released by the first consumer warp
+ch = ch[(ch[:, 2] > 0)]
+if len(ch) > 16:
+    c = ch[12:-2]
+    have_p = c[:, 0] > 0
+    print(f"CTA 0, {len(c)} chunks: issue cost med {int(np.median((c[:,1]-c[:,0])[have_p]))} ns; issued->landed med {int(np.median((c[:,2]-c[:,1])[have_p]))} ns; "
+          f"landed->released med {int(np.median(c[:,3]-c[:,2]))} ns; chunk period med {int(np.median(np.diff(c[:,2])))} ns")
+    nxt = c[1:, 0] - c[:-1, 3]
