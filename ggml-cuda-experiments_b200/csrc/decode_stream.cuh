@@ -34,7 +34,7 @@ namespace b200fa {
 
 constexpr int DK_CHUNK = 64;   // keys per pipeline stage
 constexpr int DK_CWARPS = 8;   // consumer warps (two groups of four)
-constexpr int DK_PWARPS = 2;   // producer warps: one issues the K operations of a chunk, the other V and the mask rows
+constexpr int DK_PWARPS = 4;   // producer warps: K box 0 | K box 1 | V box 0 | V box 1 + mask rows (q8_0: K | - | V | mask)
 constexpr int DK_THREADS = (DK_CWARPS + DK_PWARPS) * 32;
 constexpr int DK_SLOTS = DK_CWARPS;  // cross-warp merge slots: one per consumer warp
 constexpr int DK_MASK_BYTES = 16 * 128;
@@ -171,16 +171,18 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     if (warp >= DK_CWARPS) {
         // ===================== producers =====================
         // Every TMA / bulk operation costs its issuing thread ~90 ns (measured: +10 us on the C5 shape for one extra 128-byte copy
-        // per chunk), and a q8_0 chunk is only 17 KB: a single issuer was the bottleneck of the q8_0 stream (period 690 ns per
-        // chunk, 510 of them spent issuing).  Two warps issue side by side: warp 8 the K operations, warp 9 V and the mask rows;
-        // each arms the chunk's barrier with its own byte count.  (Lanes of ONE warp issuing side by side measured slower.)
+        // per chunk): a single issuer (5 operations per f16 chunk) was a bottleneck of the stream.  Four warps issue side by side,
+        // one operation each: K box 0 | K box 1 | V box 0 | V box 1 and the mask rows (q8_0: K | nothing | V | mask rows); each
+        // arms the chunk's barrier with its own byte count.  (Lanes of ONE warp issuing side by side measured slower.)
         const int which = warp - DK_CWARPS;
+        const bool isV = which >= 2;   // warps 8, 9: K;  10, 11: V
+        const int box = which & 1;      // f16: the 64-dim box of the row this warp loads; q8_0: only box 0 exists
         if (which == 0 && lane == 0) {
             for (int s = 0; s < NS; s++) { mbar_init(&full[s], DK_PWARPS); mbar_init(&empty[s], 4); }
             fence_barrier_init();
         }
-        if (lane == 0 && (!Q8 || a.q8_lines > 0)) prefetch_tensormap(which == 0 ? &tmK : &tmV);
-        asm volatile("bar.sync 2, %0;" ::"n"(DK_PWARPS * 32) : "memory");  // the barriers exist before the other producer touches them
+        if (lane == 0 && (!Q8 || a.q8_lines > 0)) prefetch_tensormap(isV ? &tmV : &tmK);
+        asm volatile("bar.sync 2, %0;" ::"n"(DK_PWARPS * 32) : "memory");  // the barriers exist before the other producers touch them
         int pu = (int)(start / a.cph), pch = (int)(start - (long long)pu * a.cph);  // unit / chunk of the next issue
         auto issue = [&](int i) {
             const int u = pu, ch = pch;
@@ -188,15 +190,17 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv, ik3 = iq3 / p.rk3;
             const int key0 = ch * DK_CHUNK;
             const int stage = i % NS;
-            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes + (which == 0 ? 0 : Geo::kVOff);  // this producer's half of the stage
-            uint8_t* sp = smem + stage * Geo::kStageBytes + (which == 0 ? 0 : Geo::kVOff);
+            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes + (isV ? Geo::kVOff : 0);  // this producer's half of the stage
+            uint8_t* sp = smem + stage * Geo::kStageBytes + (isV ? Geo::kVOff : 0);
             const bool whole = key0 + DK_CHUNK <= p.n_kv;
-            const int mrows = (which == 1 && a.mask_bulk && whole) ? p.n_q : 0;
-            const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
-            if constexpr (!Q8) {
-                mbar_arrive_expect_tx(&full[stage], Geo::kKBytes + mrows * 128);
-#pragma unroll
-                for (int b = 0; b < Geo::kBoxes; b++) tma_load_4d(sp + b * 8192, tm, &full[stage], 64 * b, key0, ik2, ik3);
+            const int mrows = (which == DK_PWARPS - 1 && a.mask_bulk && whole) ? p.n_q : 0;
+            const CUtensorMap* tm = isV ? &tmV : &tmK;
+            const bool has_box = Q8 ? box == 0 : box < Geo::kBoxes;  // q8_0: one operation per tensor (warps 8 and 10)
+            if (!has_box) {
+                mbar_arrive_expect_tx(&full[stage], mrows * 128);
+            } else if constexpr (!Q8) {
+                mbar_arrive_expect_tx(&full[stage], 8192 + mrows * 128);
+                tma_load_4d(sp + box * 8192, tm, &full[stage], 64 * box, key0, ik2, ik3);
             } else if (a.q8_lines > 0 && (int64_t)(ch + 1) * Geo::kKBytes <= (int64_t)a.q8_lines * 128) {
                 // q8_0, chunk inside the whole-128-byte-line part of the head: the head's rows are one contiguous byte range, which
                 // the tensor maps describe as [lines][128 B] — one box of kKBytes/128 lines per K and per V chunk (a little faster
@@ -207,8 +211,8 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 // ragged or unaligned tail of a q8_0 head: a 1-D bulk copy of the 16-byte multiple, the last few words by hand
                 const int rows = min(DK_CHUNK, p.n_kv - key0);
                 const uint32_t nbytes = (uint32_t)rows * Geo::kRowBytes, nb16 = nbytes & ~15u;
-                const char* src = which == 0 ? p.k + (int64_t)ik2 * p.nb12 + (int64_t)ik3 * p.nb13 + (int64_t)key0 * Geo::kRowBytes
-                                             : p.v + (int64_t)ik2 * p.nb22 + (int64_t)ik3 * p.nb23 + (int64_t)key0 * Geo::kRowBytes;
+                const char* src = !isV ? p.k + (int64_t)ik2 * p.nb12 + (int64_t)ik3 * p.nb13 + (int64_t)key0 * Geo::kRowBytes
+                                       : p.v + (int64_t)ik2 * p.nb22 + (int64_t)ik3 * p.nb23 + (int64_t)key0 * Geo::kRowBytes;
                 for (uint32_t o = nb16; o < nbytes; o += 4) *reinterpret_cast<uint32_t*>(sp + o) = __ldg(reinterpret_cast<const uint32_t*>(src + o));
                 mbar_arrive_expect_tx(&full[stage], nb16 + mrows * 128);
                 if (nb16 > 0) bulk_g2s(sb, src, nb16, &full[stage]);
