@@ -277,17 +277,26 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev] = true;
     }
+    // Programmatic dependent launch: this kernel may be scheduled while the previous kernel of the stream drains (it waits in-kernel,
+    // griddepcontrol.wait, before its first global access).  Off for the peer-memory variants and with B200FA_NO_PDL.
+    static const bool no_pdl = getenv("B200FA_NO_PDL") != nullptr;
+    const bool pdl = !no_pdl && a.peers == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     if (a.cluster_k > 1) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = a.cluster_k; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = a.cluster_k; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
     }
-    fa_decode_stream<D, KV, RH, EXT><<<grid, DK_THREADS, smem, st>>>(p, a, tk, tv);
-    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {

@@ -167,6 +167,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     const long long G = gridDim.x;
     const long long start = (long long)blockIdx.x * a.total / G, stop = ((long long)blockIdx.x + 1) * a.total / G;
     const int my_chunks = (int)(stop - start);
+    // Programmatic dependent launch (the host opts in per launch): the NEXT kernel of the stream may be scheduled onto SMs as this
+    // grid's CTAs retire, and runs its prologue there; every thread of this kernel in turn waits (griddepcontrol.wait, below) for
+    // the previous grid to have completed and flushed before it touches global memory.  Both are no-ops on a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp >= DK_CWARPS) {
         // ===================== producers =====================
@@ -183,6 +187,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         }
         if (lane == 0 && (!Q8 || a.q8_lines > 0)) prefetch_tensormap(isV ? &tmV : &tmK);
         asm volatile("bar.sync 2, %0;" ::"n"(DK_PWARPS * 32) : "memory");  // the barriers exist before the other producers touch them
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         int pu = (int)(start / a.cph), pch = (int)(start - (long long)pu * a.cph);  // unit / chunk of the next issue
         auto issue = [&](int i) {
             const int u = pu, ch = pch;
@@ -237,6 +242,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         if (a.cluster_k > 1) cluster_sync_all();  // every thread of the cluster takes part in the cluster barrier
         return;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
 
     // ===================== consumers =====================

@@ -234,6 +234,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_pair = p.n_head * p.n_batch;
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may take over SMs as this grid's CTAs retire
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
             mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1);
@@ -253,6 +254,9 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    // Programmatic dependent launch (see launch_prefill_persistent): everything above ran while the previous kernel of the stream
+    // was still draining; nothing below touches global memory before that kernel has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // work index -> (first 128-row tile, head, batch); heavy (late) tile pairs first
     auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) {

@@ -372,10 +372,20 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
         attr_set[dev][ai] = true;
     }
     const unsigned grid = (unsigned)(pa.n_items < sm_count ? pa.n_items : sm_count);
-    kern<<<grid, two ? 640 : PF_THREADS, smem_bytes, st>>>(p, pa, tq, tk, tv, to);
+    // programmatic dependent launch: the prologue (barrier init, TMEM allocation) may run while the previous kernel of the stream —
+    // the mask classifier, the Q conversion, or the caller's own kernel — is still draining; the kernel waits before its first
+    // global access.  The experimental two-thread variant keeps the plain launch.
+    static const bool no_pdl = getenv("B200FA_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(two ? 640 : PF_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (no_pdl || two) ? 0 : 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p, pa, tq, tk, tv, to);
     n++;
     if (launches) *launches = n;
-    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    return le == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 }  // namespace b200fa
