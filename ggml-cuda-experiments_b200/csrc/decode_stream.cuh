@@ -768,23 +768,25 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         __threadfence();
         for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
             const int R = idx / D, d = idx % D;
-            // one pass, loads batched eight records at a time (they are independent: one L2 round trip per batch)
+            // one pass, loads batched MB records at a time (they are independent: ONE L2 round trip for up to 24 contributors — with
+            // batches of 8 the merge of an 18-CTA unit took three round trips, ~7 us = a third of the per-GPU C5 step at 8 GPUs)
+            constexpr int MB = 24;
             float M = -INFINITY, L = 0.f, acc = 0.f;
-            for (int cb = 0; cb < n_contrib; cb += 8) {
-                float mm[8], ll[8], aa[8];
+            for (int cb = 0; cb < n_contrib; cb += MB) {
+                float mm[MB], ll[MB], aa[MB];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
+                for (int e = 0; e < MB; e++) {
                     const float* rec = a.rec + ((int64_t)s_tab[min(cb + e, n_contrib - 1)] * DK_REC_ROWS + R) * (D + DK_REC_PAD);
                     mm[e] = __ldcg(rec + D); ll[e] = __ldcg(rec + D + 1); aa[e] = __ldcg(rec + d);
                 }
                 float Mb = M;
 #pragma unroll
-                for (int e = 0; e < 8; e++) if (cb + e < n_contrib) Mb = fmaxf(Mb, mm[e]);
+                for (int e = 0; e < MB; e++) if (cb + e < n_contrib) Mb = fmaxf(Mb, mm[e]);
                 const float Mu = (Mb == -INFINITY) ? 0.f : Mb;
                 const float w0 = fast_exp2(M - Mu);  // M = -inf -> 0
                 L *= w0; acc *= w0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
+                for (int e = 0; e < MB; e++) {
                     if (cb + e < n_contrib) {
                         const float wt = fast_exp2(mm[e] - Mu);
                         L += ll[e] * wt; acc += aa[e] * wt;
