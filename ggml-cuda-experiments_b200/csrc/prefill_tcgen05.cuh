@@ -572,12 +572,22 @@ __global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__
     const int off = n_kv - n_q;
     int has_zero = 0, has_ninf = 0, has_other = 0, deviates = 0;
     const bool vec = ((((uintptr_t)mask | (uintptr_t)nb31) & 15) == 0) && (j + 1) * PF_BN <= n_kv;
-    if (vec) {  // aligned, whole tile: 16-byte loads, 8 mask values each
-        for (int idx = threadIdx.x; idx < PF_BM * (PF_BN / 8); idx += blockDim.x) {
+    if (vec) {  // aligned, whole tile: 16-byte loads, 8 mask values each — all eight loads of a thread in flight at once (a rolled
+                // loop made this kernel eight dependent DRAM round trips long: 8 us for C3's 8 MB mask)
+        constexpr int kIters = PF_BM * (PF_BN / 8) / 256;
+        uint4 v[kIters];
+#pragma unroll
+        for (int it = 0; it < kIters; it++) {
+            const int idx = threadIdx.x + it * 256;
+            const int r = qt * PF_BM + idx / (PF_BN / 8), col = j * PF_BN + (idx % (PF_BN / 8)) * 8;
+            v[it] = r < n_q ? ld_nc_v4(mask + (int64_t)r * nb31 + (int64_t)col * 2) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int it = 0; it < kIters; it++) {
+            const int idx = threadIdx.x + it * 256;
             const int r = qt * PF_BM + idx / (PF_BN / 8), col = j * PF_BN + (idx % (PF_BN / 8)) * 8;
             if (r >= n_q) continue;
-            const uint4 v = *reinterpret_cast<const uint4*>(mask + (int64_t)r * nb31 + (int64_t)col * 2);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const uint32_t bits = (w[e >> 1] >> (16 * (e & 1))) & 0xffffu;
