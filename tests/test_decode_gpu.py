@@ -337,3 +337,43 @@ def test_fused_seqpar_step_world_1():
             assert_close(out.cpu().numpy().reshape(ref.shape), ref, f"fused seqpar step {step}")
     finally:
         xs[0].close()
+
+
+def test_graph_replay_back_to_back_calls_share_a_workspace():
+    """Decode and prefill calls recorded back to back in one CUDA graph on one workspace (programmatic dependent launch lets each
+    kernel's prologue overlap the previous kernel's tail; the split-KV counters are reused from call to call): every replay must
+    reproduce the eagerly computed results."""
+    import torch
+    P = pkg()
+    shapes = [(1, 4096, 32, 32), (1, 1000, 32, 8), (1, 8192, 8, 8), (256, 256, 4, 4), (1, 4096, 32, 32)]
+    calls = []
+    ws_bytes = 0
+    for i, (n_q, n_kv, H, Hk) in enumerate(shapes):
+        Q, K, V = synth_qkv(128, n_q, n_kv, H, Hk, seeds=(50 + i, 60 + i, 70 + i))
+        q, k, v = to_dev(Q), to_dev(K), to_dev(V)
+        ws_bytes = max(ws_bytes, P.workspace_size(0, 1, 128, n_q, H, 1, n_kv, Hk, 1))
+        calls.append((q, k, v))
+    ws = P.Workspace(ws_bytes)
+    eager = []
+    for (q, k, v) in calls:
+        eager.append(P.flash_attn_ext(q, k, v, None, workspace=ws, flags=P.FLAG_WORKSPACE_ZEROED).clone())
+    torch.cuda.synchronize()
+    outs = [torch.zeros_like(e) for e in eager]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for (q, k, v), o in zip(calls, outs):  # warm-up on the capture stream
+            P.flash_attn_ext(q, k, v, None, dst=o, workspace=ws, flags=P.FLAG_WORKSPACE_ZEROED, stream=s)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for rep in range(3):
+                for (q, k, v), o in zip(calls, outs):
+                    P.flash_attn_ext(q, k, v, None, dst=o, workspace=ws, flags=P.FLAG_WORKSPACE_ZEROED, stream=s)
+    for rep in range(4):
+        for o in outs:
+            o.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        for e, o in zip(eager, outs):
+            assert torch.equal(e, o), f"replay {rep}: graph result differs from the eager one"
