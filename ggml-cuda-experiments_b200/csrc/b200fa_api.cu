@@ -106,7 +106,27 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
         const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;
         pl.cls_bytes = align_up((size_t)(qt * kt), 256);
         pl.ctr_bytes = kCtrRegion;
-        pl.total = pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes;
+        // Split-KV prefill: fewer work items than SMs and a long KV range (chunked prefill, long-context continuation): cut every
+        // item's KV tiles into n_splits segments, each its own work item emitting (O~, m, l) rows, merged by a second launch.
+        // Pick the segment count with the shortest makespan (waves / segments) among 2..16 with >= 8 KV tiles per segment and at
+        // most 128 MB of partial rows.
+        const int64_t n_items = ((qt + 1) / 2) * n_head * n_batch;
+        static const bool no_split = getenv("B200FA_PREFILL_NO_SPLIT") != nullptr;
+        if (!no_split && n_items < sm_count && kt >= 16 && kt <= PP_MAX_KV_TILES && (sh.Dr == 0 || sh.Dr == 128)) {
+            const size_t row_bytes = (size_t)(n_q * n_head * n_batch) * (128 + 4) * 4;
+            int best = 1;
+            double best_t = 1.0;
+            for (int s = 2; s <= 16 && kt / s >= 8 && row_bytes * s <= ((size_t)128 << 20); s++) {
+                const int64_t units = n_items * s, waves = (units + sm_count - 1) / sm_count;
+                const double t = (double)waves / s;
+                if (t < best_t - 1e-9) { best_t = t; best = s; }
+            }
+            if (best > 1) {
+                pl.n_splits = best;
+                pl.part_bytes = align_up(row_bytes * best, 256);
+            }
+        }
+        pl.total = pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes + pl.part_bytes;
         return pl;
     }
     if (allow_stream && stream_eligible(sh, sizing)) {
@@ -455,7 +475,9 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
             rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
         } else {
             if (!(flags & B200FA_FLAG_WORKSPACE_ZEROED) && cudaMemsetAsync(ws + kPrefillCtrOff, 0, 256, st) != cudaSuccess) return B200FA_ERR_CUDA;
-            rc = launch_prefill_persistent(p, ws + pl.ctr_bytes, pl.qf16_bytes, reinterpret_cast<unsigned int*>(ws + kPrefillCtrOff), di.sm_count, st, &launches);
+            const bool split = pl.n_splits > 1 && !per_cta;
+            rc = launch_prefill_persistent(p, ws + pl.ctr_bytes, pl.qf16_bytes, reinterpret_cast<unsigned int*>(ws + kPrefillCtrOff), di.sm_count, st, &launches,
+                                           split ? pl.n_splits : 1, split ? reinterpret_cast<float*>(ws + pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes) : nullptr);
         }
         g_last_launches = launches;
         return rc;

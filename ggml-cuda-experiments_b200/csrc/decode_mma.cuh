@@ -709,6 +709,30 @@ __global__ void __launch_bounds__(D) fa_combine(const float* __restrict__ part, 
     else reinterpret_cast<float*>(dst)[row * D + d] = y;
 }
 
+// The same merge for the split-KV prefill: records are [part][row][D + 4] (16-byte aligned rows written by TMA stores: O~[D], m, l,
+// 2 unused), dst rows are Dr wide.
+template <int D>
+__global__ void __launch_bounds__(D) fa_combine_pad(const float* __restrict__ part, int n_parts, int64_t n_rows, void* __restrict__ dst,
+                                                    int dst_type, int Dr) {
+    const int64_t row = blockIdx.x;
+    const int d = threadIdx.x;
+    float M = -INFINITY;
+    for (int s = 0; s < n_parts; s++) M = fmaxf(M, __ldcg(part + ((int64_t)s * n_rows + row) * (D + 4) + D));
+    const float Mu = (M == -INFINITY) ? 0.f : M;
+    float L = 0.f, acc = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < n_parts; s++) {
+        const float* rec = part + ((int64_t)s * n_rows + row) * (D + 4);
+        const float wt = __expf(__ldcg(rec + D) - Mu);
+        L += __ldcg(rec + D + 1) * wt;
+        acc += __ldcg(rec + d) * wt;
+    }
+    const float y = L > 0.f ? acc / L : 0.f;
+    if (d >= Dr) return;
+    if (dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(dst)[row * Dr + d] = __float2half_rn(y);
+    else reinterpret_cast<float*>(dst)[row * Dr + d] = y;
+}
+
 // ---- cross-GPU combine over peer-mapped memory (NVLink stores), no NCCL on the path ----
 // Exchange buffer, identical on every rank (zero-filled once):
 //   header (256 B): [0] arrival counter (monotonic: += 1 per rank per step, written by every rank)

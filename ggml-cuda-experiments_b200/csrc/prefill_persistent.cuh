@@ -39,6 +39,10 @@ struct PpArgs {
     unsigned int* counters;    // [0] next item to hand out (beyond the first gridDim.x), [1] CTAs finished, [2] mask tiles that deviate
                                // from the exactly-causal pattern (written by fa_mask_classify); all zero between calls
     int detect_causal;         // a mask tensor was scanned: if counters[2] == 0 it is the causal mask and is synthesised instead of read
+    // split-KV prefill (few items, long KV — chunked prefill): a work index is item * n_seg + segment; segment s covers KV tiles
+    // [s*T/n_seg, (s+1)*T/n_seg) and the epilogue emits unnormalised (O~, m, l) rows [segment][row][D + 4] (tmO describes that
+    // buffer) which fa_combine_pad merges.  n_seg == 1: the plain kernel.
+    int n_seg;
 };
 
 // Role bodies shared by the persistent kernels (one or two softmax threads per query row).
@@ -53,7 +57,7 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
                                                  const CUtensorMap& tmK, const CUtensorMap& tmV) {
     using namespace ptx;
     const PfArgs& a = pa.f;
-    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w, qt0, iq2, iq3); };
+    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w / pa.n_seg, qt0, iq2, iq3); };
     const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
     // ===================== producer warp: hands out items, builds their schedule, streams Q / K / V =====================
     if (lane == 0) { prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); }
@@ -81,6 +85,12 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
                 lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
                 hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
             }
+        }
+        if (w >= 0 && pa.n_seg > 1) {  // this work index is one KV segment of its item
+            const int seg = w % pa.n_seg;
+            lo = max(lo, (int)((long long)seg * a.n_kv_tiles / pa.n_seg));
+            hi = min(hi, (int)((long long)(seg + 1) * a.n_kv_tiles / pa.n_seg));
+            if (lo >= hi) { lo = a.n_kv_tiles; hi = 0; }
         }
         if (lane == 0) { sm.it_w[slot] = w; sm.it_jlo[slot] = lo; sm.it_jhi[slot] = hi; }
         __syncwarp();
@@ -119,7 +129,7 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
 __device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& pa, PpShared& sm, uint32_t tmem, const int t) {
     using namespace ptx;
     const PfArgs& a = pa.f;
-    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w, qt0, iq2, iq3); };
+    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w / pa.n_seg, qt0, iq2, iq3); };
     // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 query tile 1 =====================
     if (elect_one()) {
         constexpr uint32_t idesc_qk = make_idesc_f16(PF_BM, 64, 0, 0);
@@ -260,8 +270,9 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
 
     // work index -> (first 128-row tile, head, batch); heavy (late) tile pairs first
     auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) {
-        qt0 = 2 * (a.n_q_pairs - 1 - w / per_pair);
-        const int rem = w % per_pair;
+        const int item = w / pa.n_seg;
+        qt0 = 2 * (a.n_q_pairs - 1 - item / per_pair);
+        const int rem = item % per_pair;
         iq2 = rem % p.n_head; iq3 = rem / p.n_head;
     };
 
@@ -458,20 +469,27 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             __syncwarp();
             if (g > 0 && lane == 0) mbar_arrive(&sm.o_free[t]);  // O_t is in registers: the next item may accumulate into it
             if (tl) tl[2] = clock64();
-            const float inv_l = l > 0.f ? 1.f / l : 0.f;
+            const bool partial = pa.n_seg > 1;  // split-KV: unnormalised O~ plus (m, l) go to the partial buffer (tmO describes it)
+            const float inv_l = partial ? 1.f : (l > 0.f ? 1.f / l : 0.f);
             if (qt < a.n_q_tiles) {
                 // Each thread holds one whole output row.  Per pass the warp parks a 64-byte piece of its 32 rows in 2 KB of
                 // shared memory (16-byte chunk c of row i at chunk position c ^ ((i >> 1) & 3) = the TMA 64-byte swizzle) and
                 // one lane hands the 32 x 64-byte box to the TMA engine: the store to HBM is asynchronous, rows past n_q are
                 // clipped by the tensor map, and the warp only waits until the engine has READ the staging buffer.
-                const bool f32out = p.dst_type == B200FA_TYPE_F32;
+                const bool f32out = partial || p.dst_type == B200FA_TYPE_F32;
                 const int row0 = q0 + (warp & 3) * 32;
-                const int n_pass = (p.Dr * (f32out ? 4 : 2) + 63) >> 6;  // 16 f32 or 32 f16 columns = 64 bytes per pass; columns past the real head size are never stored
+                // 16 f32 or 32 f16 columns = 64 bytes per pass; columns past the real head size are never stored.  Partials: a ninth
+                // pass carries (m in natural-log units, l) in columns D, D+1 (the box is clipped to the D + 4 columns of a record).
+                const int n_pass = partial ? 9 : (p.Dr * (f32out ? 4 : 2) + 63) >> 6;
+                const int c3 = partial ? (w % pa.n_seg) * p.n_batch + iq3 : iq3;
 #pragma unroll
-                for (int pass = 0; pass < 8; pass++) {
+                for (int pass = 0; pass < 9; pass++) {
                     if (pass >= n_pass) break;
                     uint4 piece[4];
-                    if (f32out) {
+                    if (pass == 8) {
+                        piece[0] = make_uint4(__float_as_uint(m_ref * 0.6931471805599453f), __float_as_uint(l), 0u, 0u);
+                        piece[1] = piece[2] = piece[3] = make_uint4(0u, 0u, 0u, 0u);
+                    } else if (f32out) {
                         const int q4 = pass >> 1, b = (pass & 1) * 16;
 #pragma unroll
                         for (int i = 0; i < 4; i++)
@@ -494,7 +512,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&tmO, stg, pass * (f32out ? 16 : 32), iq2, row0, iq3);
+                        tma_store_4d(&tmO, stg, pass * (f32out ? 16 : 32), iq2, row0, c3);
                         bulk_commit();
                     }
                 }

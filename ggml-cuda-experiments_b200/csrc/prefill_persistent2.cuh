@@ -297,8 +297,10 @@ fa_prefill_persistent2(const __grid_constant__ FaParams p, const __grid_constant
     }
 }
 
+// n_seg > 1: split-KV prefill — `part` ([n_seg][total_rows][D + 4] f32, in the workspace) receives the segments' partial rows and
+// fa_combine_pad merges them into dst in a second launch.
 inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_bytes, unsigned int* counters, int sm_count,
-                                     cudaStream_t st, int* launches) {
+                                     cudaStream_t st, int* launches, int n_seg = 1, float* part = nullptr) {
     if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PP_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
     // Head sizes below 128 (Dr, a multiple of 8) run on the same 128-wide kernel: the tensor maps describe rows of Dr elements,
     // so TMA zero-fills columns Dr..127 of every Q/K/V tile on the way in (zeros add nothing to Q.K^T, and the P.V columns they
@@ -330,7 +332,9 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
         a.cls = cls;
         pa.detect_causal = 1;
     }
-    pa.n_items = a.n_q_pairs * p.n_head * p.n_batch;
+    if (n_seg < 1 || (n_seg > 1 && (part == nullptr || p.Dr != PF_D))) return B200FA_ERR_INVALID;
+    pa.n_seg = n_seg;
+    pa.n_items = a.n_q_pairs * p.n_head * p.n_batch * n_seg;
     pa.counters = counters;
     CUtensorMap tq, tk, tv;
     if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3, 128, Dr)) return B200FA_ERR_CUDA;
@@ -340,13 +344,14 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     {   // dst [batch][n_q][n_head][D]: box = 64 bytes x 1 head x 32 rows, 64-byte swizzle (the epilogue's staging layout)
         PFN_encodeTiled enc = get_encode_tiled();
         if (!enc) return B200FA_ERR_CUDA;
-        const bool f32o = p.dst_type == B200FA_TYPE_F32;
+        const bool f32o = n_seg > 1 || p.dst_type == B200FA_TYPE_F32;
         const cuuint64_t es = f32o ? 4 : 2;
-        cuuint64_t dims[4] = {(cuuint64_t)Dr, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch};
-        cuuint64_t strides[3] = {(cuuint64_t)Dr * es, (cuuint64_t)p.n_head * Dr * es, (cuuint64_t)p.n_q * p.n_head * Dr * es};
+        const cuuint64_t rowlen = n_seg > 1 ? PF_D + 4 : Dr;  // partial records: O~[D], m, l, 2 unused; dim 3 = segment * n_batch + batch
+        cuuint64_t dims[4] = {rowlen, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch * n_seg};
+        cuuint64_t strides[3] = {rowlen * es, (cuuint64_t)p.n_head * rowlen * es, (cuuint64_t)p.n_q * p.n_head * rowlen * es};
         cuuint32_t box[4] = {(cuuint32_t)(64 / es), 1, 32, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&to, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.dst, dims, strides, box, estr,
+        if (enc(&to, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, n_seg > 1 ? (void*)part : p.dst, dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return B200FA_ERR_CUDA;
@@ -358,7 +363,7 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     // named barrier + shared-memory max exchange costs more than the extra warps hide); kept selectable for comparison
     static const bool two_env = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "p2");
     const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;  // ext2 score modifiers: their own instantiation
-    const bool two = two_env && Dr == PF_D && !ext;
+    const bool two = two_env && Dr == PF_D && !ext && n_seg == 1;
     auto kern = ext ? fa_prefill_persistent<2, true>
               : two ? (poly == 0 ? fa_prefill_persistent2<0> : fa_prefill_persistent2<2>)
                     : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));
@@ -384,6 +389,11 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     cfg.attrs = attr; cfg.numAttrs = (no_pdl || two) ? 0 : 1;
     const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p, pa, tq, tk, tv, to);
     n++;
+    if (le == cudaSuccess && n_seg > 1) {
+        fa_combine_pad<PF_D><<<(unsigned)p.total_rows, PF_D, 0, st>>>(part, n_seg, p.total_rows, p.dst, p.dst_type, Dr);
+        n++;
+        if (cudaGetLastError() != cudaSuccess) return B200FA_ERR_CUDA;
+    }
     if (launches) *launches = n;
     return le == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }

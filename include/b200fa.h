@@ -74,7 +74,8 @@ int b200fa_version(void); /* major*10000 + minor*100 + patch */
  *
  * Dispatch (all on the GPU):
  *   n_q * (n_head/n_head_kv) <= 64  -> split-KV register-streaming kernel, splits merged in-kernel (decode; HBM-bound)
- *   otherwise, D == 128, f16 K/V    -> tcgen05/TMEM/TMA tile kernel (prefill; tensor-bound)
+ *   otherwise, f16 K/V              -> tcgen05/TMEM/TMA tile kernel (prefill; tensor-bound); with fewer work items than SMs and a long
+ *                                      KV range the KV tiles are split into segments merged by a second launch
  *   otherwise                       -> the register-streaming kernel over 16-row groups
  * Requirements: head size D = ne00: any multiple of 8 up to 128 with f16 K/V (64 and 128 run natively; the others run
  * zero-padded on the fly on the 64/128-wide kernels, nothing is copied), 64 or 128 with q8_0 K/V and in the partial /

@@ -212,3 +212,28 @@ def test_full_size_properties_c3():
     pre = 1024
     c = P.flash_attn_ext(q[:, :, pre - 1:pre], k[:, :, :pre], v[:, :, :pre], None).cpu().numpy()   # decode-style call: row pre-1 over keys [0, pre)
     assert np.abs(c[0, 0] - a[0, pre - 1]).max() < 2e-3                     # (iii)
+
+
+# ---- split-KV prefill: fewer work items than SMs and a long KV range (chunked prefill / long-context continuation) ----
+@pytest.mark.parametrize("n_q,n_kv,H,Hk,B,kind", [
+    (256, 4096, 4, 4, 1, "none"), (256, 4096, 4, 2, 1, "causal"), (130, 3000, 3, 1, 2, "noise"), (96, 8192, 2, 2, 1, "causal"),
+    (384, 2048, 8, 8, 1, "causal"), (128, 2100, 1, 1, 1, "zeros")])
+def test_split_kv_prefill(n_q, n_kv, H, Hk, B, kind):
+    Q, K, V = synth_qkv(128, n_q, n_kv, H, Hk, n_batch=B)
+    mask = make_mask(kind, n_q, n_kv)
+    flags = pkg().FLAG_CAUSAL if kind == "causal" else 0
+    a, _ = run_both(Q, K, V, mask, flags=flags)
+    _check_dispatch()
+    n_launch = pkg().last_launch_count()
+    expect = 1 + 1 + 1 + (1 if (mask is not None and not flags) else 0)   # Q conversion + attention + combine (+ mask classifier)
+    assert n_launch == expect, f"expected {expect} launches (split-KV), got {n_launch}"
+
+
+def test_split_kv_prefill_f16_io_and_mask_tensor_only():
+    Q, K, V = synth_qkv(128, 200, 5000, 4, 4)
+    mask = make_mask("causal", 200, 5000)
+    run_both(Q, K, V, mask, q_f16=True, dst_f16=True, cache_view=True)       # mask tensor without the flag: classify + attention + combine
+    _check_dispatch()
+    assert pkg().last_launch_count() == 3
+    run_both(Q, K, V, mask, flags=pkg().FLAG_CAUSAL, q_f16=True)
+    assert pkg().last_launch_count() == 2
