@@ -67,6 +67,7 @@ struct Plan {
     size_t part_bytes = 0;   // split-KV partials / stream-K records
     size_t qf16_bytes = 0;   // f16 copy of an f32 Q (tcgen05 path)
     size_t cls_bytes = 0;    // mask tile classes (tcgen05 path)
+    size_t kvf16_bytes = 0;  // f16 copies of q8_0 K and V (tcgen05 path on a quantised cache), K then V
     size_t ctr_bytes = 0;    // counter region actually reserved
     size_t total = 0;
 };
@@ -78,6 +79,7 @@ struct Shape {
     const void* k; const void* v;
     int64_t kv_pos0, n_kv_total;
     int64_t Dr = 0;  // real head size when it differs from the structural D (0 = same)
+    int64_t n_batch_kv = 0;  // ne13 (0 = n_batch)
     bool ext = false;  // ALiBi / soft-cap requested (ext2 entry): only the persistent prefill kernel implements them
 };
 
@@ -99,7 +101,13 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     const int64_t D = sh.D, n_q = sh.n_q, n_head = sh.n_head, n_batch = sh.n_batch, n_kv = sh.n_kv, n_head_kv = sh.n_head_kv;
     const int64_t gqa = n_head / n_head_kv;
     const int64_t rows = n_q * gqa;
-    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D <= 128 && sh.kv_type == B200FA_TYPE_F16 && n_q >= 64 &&
+    // q8_0 K/V on the prefill path: dequantised once to dense f16 in the workspace (RN_f16(d*q), what the decode kernel feeds its
+    // P.V too), then the tensor-core kernel — the 16-row fallback re-reads K/V per row group and measured 20 TFLOP/s on C3's shape.
+    const int64_t nbk = sh.n_batch_kv > 0 ? sh.n_batch_kv : n_batch;
+    const size_t kv16 = sh.kv_type == B200FA_TYPE_Q8_0 ? align_up((size_t)(n_kv * n_head_kv * nbk * D * 2), 256) : 0;
+    static const bool no_q8_prefill = getenv("B200FA_NO_Q8_PREFILL") != nullptr;
+    const bool kv_ok = sh.kv_type == B200FA_TYPE_F16 || (!no_q8_prefill && (D == 64 || D == 128) && kv16 <= ((size_t)512 << 20));
+    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D <= 128 && kv_ok && n_q >= 64 &&
         n_kv <= ((sh.Dr == 0 || sh.Dr == 128) && !sh.ext ? (int64_t)PF_MAX_KV_TILES * PF_BN : (int64_t)PP_MAX_KV_TILES * PF_BN)) {
         pl.kind = kPrefill;
         if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * 128 * 2), 256);
@@ -126,7 +134,8 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
                 pl.part_bytes = align_up(row_bytes * best, 256);
             }
         }
-        pl.total = pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes + pl.part_bytes;
+        pl.kvf16_bytes = 2 * kv16;
+        pl.total = pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes + pl.part_bytes + pl.kvf16_bytes;
         return pl;
     }
     if (allow_stream && stream_eligible(sh, sizing)) {
@@ -394,9 +403,8 @@ size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01
     const DeviceInfo& di = device_info();
     const int sms = di.ok ? di.sm_count : 148;
     if (ne12 <= 0 || ne02 % ne12 || ne00 <= 0 || ne01 <= 0 || ne03 <= 0 || ne11 <= 0) return 0;
-    (void)ne13;
     if (ne00 > 128) return 0;
-    Shape sh{q_type, kv_type, ne00 <= 64 ? 64 : 128, ne01, ne02, ne03, ne11, ne12, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11, ne00};
+    Shape sh{q_type, kv_type, ne00 <= 64 ? 64 : 128, ne01, ne02, ne03, ne11, ne12, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11, ne00, ne13 > 0 ? ne13 : ne03};
     size_t m = 0;
     for (int variant = 0; variant < 5; variant++) {  // every path the two entry points can take for this shape
         const bool partial = variant == 1 || variant == 3;
@@ -429,7 +437,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     const int64_t Dp = ne00 <= 64 ? 64 : 128;  // structural head size of the decode kernels; the prefill kernel is always 128 wide
     const float max_bias = ext ? ext->max_bias : 0.f, softcap = ext ? ext->logit_softcap : 0.f;
     if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
-    Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00};
+    Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
     sh.ext = max_bias > 0.f || softcap != 0.f;
     Plan pl = make_plan(sh, flags, di.sm_count, want_partial, false);
     if (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256)) return B200FA_ERR_WORKSPACE;
@@ -470,6 +478,18 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
         g_last_dispatch = "prefill_tcgen05";
         p.D = PF_D;
         int launches = 0;
+        if (kv_type == B200FA_TYPE_Q8_0) {  // f16 copies of K and V, dense [batch][head][row][D]
+            __half* k16 = reinterpret_cast<__half*>(ws + pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes + pl.part_bytes);
+            __half* v16 = reinterpret_cast<__half*>(reinterpret_cast<char*>(k16) + pl.kvf16_bytes / 2);
+            const int64_t n_oct = ne11 * ne12 * ne13 * (ne00 / 8);
+            const unsigned gb = (unsigned)((n_oct + 255) / 256);
+            q8_rows_to_f16_kernel<<<gb, 256, 0, st>>>(p.k, k16, (int)ne00, (int)ne11, (int)ne12, n_oct, nb11, nb12, nb13);
+            q8_rows_to_f16_kernel<<<gb, 256, 0, st>>>(p.v, v16, (int)ne00, (int)ne11, (int)ne12, n_oct, nb21, nb22, nb23);
+            if (cudaGetLastError() != cudaSuccess) return B200FA_ERR_CUDA;
+            p.k = reinterpret_cast<const char*>(k16); p.v = reinterpret_cast<const char*>(v16);
+            p.kv_type = B200FA_TYPE_F16;
+            p.nb11 = p.nb21 = ne00 * 2; p.nb12 = p.nb22 = ne11 * ne00 * 2; p.nb13 = p.nb23 = ne12 * ne11 * ne00 * 2;
+        }
         static const bool per_cta = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "cta");
         if ((per_cta && p.Dr == PF_D) || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
             rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
@@ -479,7 +499,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
             rc = launch_prefill_persistent(p, ws + pl.ctr_bytes, pl.qf16_bytes, reinterpret_cast<unsigned int*>(ws + kPrefillCtrOff), di.sm_count, st, &launches,
                                            split ? pl.n_splits : 1, split ? reinterpret_cast<float*>(ws + pl.ctr_bytes + pl.qf16_bytes + pl.cls_bytes) : nullptr);
         }
-        g_last_launches = launches;
+        g_last_launches = launches + (kv_type == B200FA_TYPE_Q8_0 ? 2 : 0);
         return rc;
     }
 

@@ -67,4 +67,31 @@ __global__ void kv_append_kernel(const char* __restrict__ src, char* __restrict_
     }
 }
 
+// q8_0 K/V rows (any ne/nb strides) -> dense f16 [batch][head][row][D] with y = RN_f16(f32(d) * q): the pre-pass that lets the
+// tcgen05 prefill kernel run on a quantised KV cache.  One thread per 8 elements (five independent 16-bit loads — blocks are only
+// 2-byte aligned — and one 16-byte store); a warp-per-block version was latency-bound at 0.5 TB/s.
+__global__ void __launch_bounds__(256) q8_rows_to_f16_kernel(const char* __restrict__ src, __half* __restrict__ dst, int D, int n_rows,
+                                                             int n_head, int64_t n_oct, int64_t nb1, int64_t nb2, int64_t nb3) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // octet index over the dense output
+    if (o >= n_oct) return;
+    const int opr = D / 8;                             // octets per row
+    const int c8 = (int)(o % opr);
+    const int64_t r = o / opr;                         // dense row index ((b * n_head + h) * n_rows + row)
+    const int row = (int)(r % n_rows), h = (int)((r / n_rows) % n_head);
+    const int64_t b = r / ((int64_t)n_rows * n_head);
+    const uint16_t* blk = reinterpret_cast<const uint16_t*>(src + row * nb1 + h * nb2 + b * nb3 + (c8 >> 2) * kQ8BlockBytes);
+    const uint16_t* qs = blk + 1 + (c8 & 3) * 4;
+    const uint32_t w0 = __ldg(qs), w1 = __ldg(qs + 1), w2 = __ldg(qs + 2), w3 = __ldg(qs + 3);
+    const float d = __half2float(__ushort_as_half(__ldg(blk)));
+    const uint32_t w[4] = {w0, w1, w2, w3};
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float lo = __fmul_rn(d, (float)(int8_t)(w[i] & 0xffu)), hi = __fmul_rn(d, (float)(int8_t)((w[i] >> 8) & 0xffu));
+        const __half2 hh = __halves2half2(__float2half_rn(lo), __float2half_rn(hi));
+        out[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    *reinterpret_cast<uint4*>(dst + r * D + c8 * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 }  // namespace b200fa

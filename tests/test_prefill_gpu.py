@@ -237,3 +237,15 @@ def test_split_kv_prefill_f16_io_and_mask_tensor_only():
     assert pkg().last_launch_count() == 3
     run_both(Q, K, V, mask, flags=pkg().FLAG_CAUSAL, q_f16=True)
     assert pkg().last_launch_count() == 2
+
+
+# ---- q8_0 K/V on the prefill path: dequantised once to f16 in the workspace, then the tensor-core kernel ----
+@pytest.mark.parametrize("D,n_q,n_kv,H,Hk,B,kind", [
+    (128, 256, 256, 4, 4, 1, "causal"), (128, 300, 517, 4, 2, 2, "noise"), (64, 200, 264, 4, 4, 1, "causal"),
+    (128, 130, 130, 3, 1, 1, "none"), (128, 256, 4096, 4, 4, 1, "causal")])
+def test_q8_0_prefill(D, n_q, n_kv, H, Hk, B, kind):
+    Q, K, V = synth_qkv(D, n_q, n_kv, H, Hk, n_batch=B)
+    mask = make_mask(kind, n_q, n_kv)
+    flags = pkg().FLAG_CAUSAL if kind == "causal" else 0
+    run_both(Q, K, V, mask, flags=flags, q8=True)
+    _check_dispatch()
