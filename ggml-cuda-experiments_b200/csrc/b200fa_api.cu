@@ -96,6 +96,16 @@ bool stream_eligible(const Shape& sh, bool sizing) {
     return (((uintptr_t)sh.k | (uintptr_t)sh.v | (uintptr_t)sh.nb12 | (uintptr_t)sh.nb13 | (uintptr_t)sh.nb22 | (uintptr_t)sh.nb23) % 16) == 0;
 }
 
+// How many virtual KV heads a real one is split into so that a 17..64-row GQA burst fits the stream kernel's 16 rows (1 = no split)
+int virtual_head_split(int64_t n_q, int64_t n_head, int64_t n_head_kv, int64_t n_batch) {
+    static const bool no_vh = getenv("B200FA_NO_VIRTUAL_HEADS") != nullptr;
+    const int64_t gqa = n_head / n_head_kv, rows = n_q * gqa;
+    if (no_vh || rows <= 16 || rows > 64 || n_q > 16 || n_head_kv * n_batch * 8 > 65536) return 1;
+    for (int dv = 2; dv <= gqa; dv++)
+        if (gqa % dv == 0 && n_q * (gqa / dv) <= 16) return dv;
+    return 1;
+}
+
 Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial_out, bool sizing, bool allow_stream = true) {
     Plan pl;
     const int64_t D = sh.D, n_q = sh.n_q, n_head = sh.n_head, n_batch = sh.n_batch, n_kv = sh.n_kv, n_head_kv = sh.n_head_kv;
@@ -340,8 +350,8 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     { static const bool nb = getenv("B200FA_NO_MASK_BULK") != nullptr; if (nb) a.mask_bulk = 0; }
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {
-        if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
-        if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
+        if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv / p.kv_div, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
+        if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv / p.kv_div, p.n_batch_kv, p.nb21, p.nb22, p.nb23, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
     }
     const bool q8 = p.kv_type == B200FA_TYPE_Q8_0;
     if (q8) {
@@ -350,8 +360,8 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
         const int64_t lines = (int64_t)p.n_kv * (p.D / kQ8BlockElems * kQ8BlockBytes) / 128;
         if (!no_lines && lines > 0) {
             const int box_lines = DK_CHUNK * (p.D / kQ8BlockElems * kQ8BlockBytes) / 128;
-            if (!make_line_map(&tk, p.k, lines, p.n_head_kv, p.n_batch_kv, p.nb12, p.nb13, box_lines)) return B200FA_ERR_CUDA;
-            if (!make_line_map(&tv, p.v, lines, p.n_head_kv, p.n_batch_kv, p.nb22, p.nb23, box_lines)) return B200FA_ERR_CUDA;
+            if (!make_line_map(&tk, p.k, lines, p.n_head_kv / p.kv_div, p.n_batch_kv, p.nb12, p.nb13, box_lines)) return B200FA_ERR_CUDA;
+            if (!make_line_map(&tv, p.v, lines, p.n_head_kv / p.kv_div, p.n_batch_kv, p.nb22, p.nb23, box_lines)) return B200FA_ERR_CUDA;
             a.q8_lines = (int)(lines > 0x7fffffff ? 0x7fffffff : lines);
         }
     }
@@ -413,6 +423,14 @@ size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01
         const Plan pl = make_plan(sh, f, sms, partial, true, stream);
         if (pl.total > m) m = pl.total;
     }
+    if (const int dv = virtual_head_split(ne01, ne02, ne12, ne03); dv > 1) {  // the virtual-head stream plan has more units and slots
+        Shape sv = sh;
+        sv.n_head_kv = ne12 * dv;
+        for (int partial = 0; partial < 2; partial++) {
+            const Plan pl = make_plan(sv, flags, sms, partial != 0, true, true);
+            if (pl.total > m) m = pl.total;
+        }
+    }
     return m + 256;
 }
 
@@ -439,6 +457,16 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
     Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
     sh.ext = max_bias > 0.f || softcap != 0.f;
+    // 17..64 rows per KV head from a GQA group (a burst of up to 16 query positions, e.g. speculative decoding): split every real
+    // KV head into kv_div VIRTUAL heads of gqa / kv_div q heads each, so that a unit has <= 16 rows and the stream kernel applies.
+    // K/V are streamed kv_div times, but by CTAs working side by side: the repeats are L2 hits (8 positions x GQA 4, batch 8,
+    // KV 8192: 190 us on the 16-row-group fallback -> 134 us).
+    int kv_div = virtual_head_split(ne01, ne02, ne12, ne03);
+    if (kv_div > 1) {
+        Shape sv = sh;
+        sv.n_head_kv = ne12 * kv_div;
+        if (stream_eligible(sv, false)) sh = sv; else kv_div = 1;
+    }
     Plan pl = make_plan(sh, flags, di.sm_count, want_partial, false);
     if (!workspace || workspace_bytes < pl.total || ((uintptr_t)workspace % 256)) return B200FA_ERR_WORKSPACE;
     char* ws = (char*)workspace;
@@ -451,6 +479,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.D = (int)Dp; p.Dr = (int)ne00; p.n_q = (int)ne01; p.n_head = (int)ne02; p.n_batch = (int)ne03;
     p.n_kv = (int)ne11; p.n_head_kv = (int)ne12; p.n_batch_kv = (int)ne13;
     p.gqa = (int)(ne02 / ne12); p.rk3 = (int)(ne03 / ne13);
+    p.kv_div = 1;
     p.nb01 = nb01; p.nb02 = nb02; p.nb03 = nb03;
     p.nb11 = nb11; p.nb12 = nb12; p.nb13 = nb13;
     p.nb21 = nb21; p.nb22 = nb22; p.nb23 = nb23;
@@ -508,6 +537,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
         if (cudaMemsetAsync(ws, 0, align_up(pl.n_counters * 4, 256), st) != cudaSuccess) return B200FA_ERR_CUDA;
     }
     if (pl.kind == kStream) {
+        if (kv_div > 1) { p.kv_div = kv_div; p.n_head_kv = (int)ne12 * kv_div; p.gqa = (int)(ne02 / ne12) / kv_div; }
         g_last_dispatch = want_partial ? "decode_stream_partial" : "decode_stream";
         return run_stream(p, pl, ws, st);
     }

@@ -192,7 +192,8 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         auto issue = [&](int i) {
             const int u = pu, ch = pch;
             if (++pch == a.cph) { pch = 0; pu++; }
-            const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv, ik3 = iq3 / p.rk3;
+            const int iq3 = u / p.n_head_kv, ik3 = iq3 / p.rk3;
+            const int ik2 = (u % p.n_head_kv) / p.kv_div;  // the REAL kv head whose K/V this (possibly virtual) unit streams
             const int key0 = ch * DK_CHUNK;
             const int stage = i % NS;
             const uint32_t sb = stages_u32 + stage * Geo::kStageBytes + (isV ? Geo::kVOff : 0);  // this producer's half of the stage
