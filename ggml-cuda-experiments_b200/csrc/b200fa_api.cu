@@ -117,7 +117,9 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     const size_t kv16 = sh.kv_type == B200FA_TYPE_Q8_0 ? align_up((size_t)(n_kv * n_head_kv * nbk * D * 2), 256) : 0;
     static const bool no_q8_prefill = getenv("B200FA_NO_Q8_PREFILL") != nullptr;
     const bool kv_ok = sh.kv_type == B200FA_TYPE_F16 || (!no_q8_prefill && (D == 64 || D == 128) && kv16 <= ((size_t)512 << 20));
-    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && rows > 64 && D <= 128 && kv_ok && n_q >= 64 &&
+    // More than 16 query positions: the tensor-core kernel, even when a 128-row tile is mostly padding (n_q = 32 against 8 K keys:
+    // 122 us on the 16-row-group fallback, which re-reads K/V per group, vs ~40 us here with the KV range split over the SMs).
+    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && n_q > 16 && D <= 128 && kv_ok &&
         n_kv <= ((sh.Dr == 0 || sh.Dr == 128) && !sh.ext ? (int64_t)PF_MAX_KV_TILES * PF_BN : (int64_t)PP_MAX_KV_TILES * PF_BN)) {
         pl.kind = kPrefill;
         if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * 128 * 2), 256);
