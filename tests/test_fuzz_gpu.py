@@ -45,3 +45,40 @@ def test_random_shape(seed):
     flags = pkg().FLAG_CAUSAL if (c["mask_kind"] == "causal" and c["flag"]) else 0
     run_both(Q, K, V, mask, flags=flags, q_f16=c["q_f16"], dst_f16=c["dst_f16"], cache_view=c["cache_view"], q8=c["q8"],
              mask_pad=32 if c["flag"] else None, what=str(c))
+
+
+def _case2(seed):
+    """Shapes around the dispatch boundaries added late in round 1: bursts on virtual KV heads, small n_q on the tile kernel,
+    split-KV prefill (few items, long KV), q8_0 on the prefill path, padded head sizes everywhere."""
+    r = np.random.RandomState(1000 + seed)
+    D = int(r.choice([128, 128, 64, 80, 96, 40]))
+    gqa = int(r.choice([1, 2, 4, 8]))
+    Hk = int(r.choice([1, 2, 3]))
+    H = Hk * gqa
+    B = int(r.choice([1, 1, 2]))
+    family = r.choice(["vheads", "small_q", "chunk", "chunk"])
+    if family == "vheads":
+        n_q = int(r.choice([2, 3, 5, 8, 11, 16]))
+        n_kv = int(r.choice([n_q + 3, 200, 1000, 2500]))
+    elif family == "small_q":
+        n_q = int(r.choice([17, 20, 33, 48, 63, 64, 65]))
+        n_kv = int(r.choice([n_q, 130, 700, 1500]))
+    else:
+        n_q = int(r.choice([17, 64, 100, 128, 200, 256]))
+        n_kv = int(r.choice([2048, 2100, 3000, 4200]))
+    mask_kind = str(r.choice(["none", "zeros", "noise", "causal", "causal"]))
+    if mask_kind == "causal" and n_kv < n_q:
+        mask_kind = "noise"
+    q8 = bool(r.rand() < 0.35) and D in (64, 128)
+    return dict(D=D, n_q=n_q, n_kv=n_kv, H=H, Hk=Hk, B=B, mask_kind=mask_kind, q8=q8, q_f16=bool(r.rand() < 0.4),
+                dst_f16=bool(r.rand() < 0.3), cache_view=bool(r.rand() < 0.4) and not q8, flag=bool(r.rand() < 0.5), seed=seed)
+
+
+@pytest.mark.parametrize("seed", list(range(72)))
+def test_random_shape_dispatch_boundaries(seed):
+    c = _case2(seed)
+    Q, K, V = synth_qkv(c["D"], c["n_q"], c["n_kv"], c["H"], c["Hk"], n_batch=c["B"], seeds=(seed + 11, seed + 12, seed + 13))
+    mask = make_mask(c["mask_kind"], c["n_q"], c["n_kv"])
+    flags = pkg().FLAG_CAUSAL if (c["mask_kind"] == "causal" and c["flag"]) else 0
+    run_both(Q, K, V, mask, flags=flags, q_f16=c["q_f16"], dst_f16=c["dst_f16"], cache_view=c["cache_view"], q8=c["q8"],
+             mask_pad=32 if c["flag"] else None, what=str(c))
