@@ -341,6 +341,34 @@ def main():
                 "frac_of_nominal_8TBs": nbytes / (t * 1e-3) / 1e9 / 8000.0, "kv_bytes": nbytes, "launches_per_step": nl, "dispatch": disp,
                 "l2": f"{nsets} rotating K/V sets of {nbytes / 1e6:.0f} MB"}
 
+    def run_next_rows():
+        """Shapes either side of the configs (SURVEY.md §8f row 3 and the dispatch boundaries): chunked prefill against a long
+        cache (split-KV prefill), prefill on a q8_0 cache, a speculative-decoding burst under GQA (virtual KV heads)."""
+        out = {}
+        def one(name, n_q, n_kv, Hq, Hk, B, causal, q8, note):
+            nsets = 2
+            ks = [rand_f16((B, Hk, n_kv, D), 200 + s) for s in range(nsets)]
+            vs = [rand_f16((B, Hk, n_kv, D), 210 + s) for s in range(nsets)]
+            if q8:
+                ks = [P.quantize_q8_0(k) for k in ks]; vs = [P.quantize_q8_0(v) for v in vs]
+            q = rand_f16((B, Hq, n_q, D), 220)
+            dst = torch.empty((B, n_q, Hq, D), dtype=torch.float32, device=dev)
+            ws = P.Workspace(P.workspace_size(P.TYPE_F16, P.TYPE_Q8_0 if q8 else P.TYPE_F16, D, n_q, Hq, B, n_kv, Hk, B))
+            flags = (P.FLAG_CAUSAL if causal else 0) | P.FLAG_WORKSPACE_ZEROED
+            def step(i):
+                P.flash_attn_ext(q, ks[i % nsets], vs[i % nsets], None, dst=dst, flags=flags, workspace=ws)
+            step(0); torch.cuda.synchronize()
+            nl = P.last_launch_count(); disp = P.last_dispatch()
+            _, t = time_steps(step, 40, 4, chunk=10)
+            fl = 4.0 * B * Hq * n_q * n_kv * D * (0.5 if (causal and n_q == n_kv) else 1.0)
+            kvb = 2.0 * B * Hk * n_kv * (136 if q8 else 256)
+            out[name] = {"config": note, "us_per_step": t * 1e3, "tflops": fl / (t * 1e-3) / 1e12, "kv_gbps": kvb / (t * 1e-3) / 1e9,
+                         "dispatch": disp, "launches_per_step": nl}
+        one("chunked_prefill_256x32k", 256, 32768, 32, 32, 1, False, False, "256 new queries against a 32K f16 cache, 32 heads (split-KV prefill)")
+        one("prefill_2k_q8_0_cache", 2048, 2048, 32, 32, 1, True, True, "C3's shape with q8_0 K/V (dequantised once to f16 workspace copies)")
+        one("burst_8x_gqa4_b8_kv8192", 8, 8192, 32, 8, 8, False, False, "8 query positions x GQA 4 = 32 rows per KV head, batch 8, KV 8192 f16 (virtual KV heads)")
+        return out
+
     def run_c4():
         Hq, Hk, B, n_kv = 32, 8, 64, 8192
         hs = P.head_shard(Hq, Hk, rank, world)  # head-parallel: this rank owns a band of kv heads (+ their 4 q heads each)
@@ -427,7 +455,7 @@ def main():
                 "l2": f"{nsets} rotating q8_0 K/V sets of {per_gpu / 1e6:.0f} MB per GPU"}
 
     if not (args.quick or args.no_extras):
-        for name, fn in (("c2_decode_32k_kv", run_c2_32k), ("c3_prefill", run_c3), ("c4_gqa_decode", run_c4), ("c5_q8_0_split_kv", run_c5)):
+        for name, fn in (("c2_decode_32k_kv", run_c2_32k), ("c3_prefill", run_c3), ("c4_gqa_decode", run_c4), ("c5_q8_0_split_kv", run_c5)) + ((("next_rows", run_next_rows),) if world == 1 else ()):
             try:
                 results[name] = fn()
             except Exception as e:  # noqa: BLE001
