@@ -3,7 +3,8 @@
 //
 // Replaces the reference's flash_attn_row<128,8,2,256> / flash_attn_row_fast (flash_row_float.h:4-413) AND
 // its fa_reduce<128,nw> (flash_row_float.h:415-472) for every call with n_q * (n_head / n_head_kv) <= 16 rows
-// per KV head (single-token decode of MHA/GQA models, short speculative bursts).
+// per KV head (single-token decode of MHA/GQA models, short speculative bursts); GQA bursts of 17..64 rows run as virtual KV
+// heads of <= 16 rows (FaParams::kv_div).
 //
 // Work decomposition ("stream-K"): a *unit* is one (kv head, batch) pair; its keys are cut into 64-key
 // chunks; all chunks of all units form one flat list that is divided evenly over the grid (one CTA per
@@ -12,11 +13,12 @@
 // CTA emits an (O~, m, l) record; the last CTA to finish a unit (arrival counter) merges the records,
 // which is the reference's fa_reduce algebra done in fp32.
 //
-// CTA = 8 consumer warps + 1 producer warp.
-//   producer (one elected lane): per chunk, waits for a free stage, then issues
-//       f16  : 2*D/64 cp.async.bulk.tensor loads (64 keys x 64 dims, 128B swizzle) from the ne/nb-strided tensors,
-//       q8_0 : two cp.async.bulk copies of the raw 34-byte blocks (rows must be contiguous),
-//       plus one 128-byte bulk copy per query row of the mask; all complete on the stage's mbarrier.
+// CTA = 8 consumer warps + 4 producer warps (one elected lane each; a TMA operation costs its issuing thread ~90 ns, so the
+// operations of a chunk are issued side by side).
+//   producers: per chunk, wait for a free stage, then issue
+//       f16  : 2*D/64 cp.async.bulk.tensor loads (64 keys x 64 dims, 128B swizzle) from the ne/nb-strided tensors, one per warp,
+//       q8_0 : one box per tensor of the head's contiguous 34-byte-block rows seen as [lines][128 B] (ragged tails: 1-D bulk copies),
+//       plus one 128-byte bulk copy per query row of the mask; all complete on the stage's mbarrier (one arrival per producer).
 //   consumers: chunk j belongs to warp group j & 1; warp (w & 3) of the group takes keys 16*(w&3)..+15 of it,
 //       reads its mma.sync fragments straight out of the swizzled stage (conflict-light 128-bit LDS), frees
 //       the stage, and does QK^T, online softmax and PV in registers — the same permuted-contraction
