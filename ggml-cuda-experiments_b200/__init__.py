@@ -7,7 +7,7 @@ device memory.  There is no CPU or PyTorch compute path: importing works anywher
 raises if libb200fa.so is missing or no sm_100 device is present.
 """
 from .api import (  # noqa: F401
-    FLAG_CAUSAL, FLAG_NO_TCGEN05, FLAG_WORKSPACE_ZEROED, TYPE_F16, TYPE_F32, TYPE_Q8_0, B200FAError, ExtParams, Workspace, dequantize_q8_0,
+    FLAG_CAUSAL, FLAG_NO_TCGEN05, FLAG_WORKSPACE_ZEROED, TYPE_F16, TYPE_F32, TYPE_Q8_0, B200FAError, ExtParams, PlanInfo, PLAN_PREFILL, PLAN_ROWS16, PLAN_STREAM, plan, Workspace, dequantize_q8_0,
     flash_attn_ext, flash_attn_ext_raw, flash_attn_partial, flash_attn_partial_scatter, flash_attn_seqpar, kv_cache_append, merge_partials_wait, PeerExchange, last_dispatch, last_launch_count, lib, merge_partials,
     quantize_q8_0, workspace_size)
 from .build import build  # noqa: F401

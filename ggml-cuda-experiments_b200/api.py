@@ -129,6 +129,27 @@ class ExtParams(C.Structure):
     _fields_ = [("max_bias", C.c_float), ("logit_softcap", C.c_float)]
 
 
+class PlanInfo(C.Structure):
+    """b200fa_plan_info."""
+    _fields_ = [("kind", C.c_int32), ("kv_div", C.c_int32), ("n_splits", C.c_int32), ("grid", C.c_int32), ("cluster_k", C.c_int32),
+                ("reserved", C.c_int32), ("kv_f16_copy_bytes", C.c_int64), ("workspace_bytes", C.c_int64)]
+
+
+PLAN_PREFILL, PLAN_STREAM, PLAN_ROWS16 = 0, 1, 2
+
+
+def plan(q_type, kv_type, D, n_q, n_head, n_batch, n_kv, n_head_kv, n_batch_kv=None, flags=0, sm_count=148) -> PlanInfo:
+    """The host-side plan for a shape (no GPU needed): kernel family, virtual heads, splits, grid, workspace."""
+    l = lib()
+    l.b200fa_plan.restype = C.c_int
+    l.b200fa_plan.argtypes = [C.c_int, C.c_int] + [C.c_int64] * 7 + [C.c_uint32, C.c_int, C.POINTER(PlanInfo)]
+    info = PlanInfo()
+    rc = l.b200fa_plan(q_type, kv_type, D, n_q, n_head, n_batch, n_kv, n_head_kv, n_batch_kv or n_batch, flags, sm_count, C.byref(info))
+    if rc != 0:
+        raise B200FAError(rc, "b200fa_plan")
+    return info
+
+
 def flash_attn_ext_raw(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb,
                        flags, ws_ptr, ws_bytes, stream_ptr, max_bias: float = 0.0, logit_softcap: float = 0.0) -> int:
     """The ABI call.  q,k,v,mask,dst are device addresses (ints); returns the status code."""

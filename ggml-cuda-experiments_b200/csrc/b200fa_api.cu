@@ -566,6 +566,37 @@ int b200fa_flash_attn_ext(const void* q, const void* k, const void* v, const voi
                        workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// The host-side decision for a shape, without touching a device: which kernel family, how the work is cut, how much workspace.
+// Mirrors attn_common's planning (no pointers: q8_0 rows are assumed contiguous and aligned, the modifiers off).
+int b200fa_plan(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03, int64_t ne11, int64_t ne12,
+                int64_t ne13, uint32_t flags, int sm_count, b200fa_plan_info* out) {
+    if (!out || sm_count < 1) return B200FA_ERR_INVALID;
+    if (ne00 <= 0 || ne01 <= 0 || ne02 <= 0 || ne03 <= 0 || ne11 <= 0 || ne12 <= 0 || ne13 <= 0 || ne02 % ne12 || ne03 % ne13) return B200FA_ERR_INVALID;
+    if (ne00 % 8 || ne00 > 128) return B200FA_ERR_UNSUPPORTED;
+    if (kv_type == B200FA_TYPE_Q8_0 && ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
+    if (kv_type != B200FA_TYPE_F16 && kv_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
+    const int64_t Dp = ne00 <= 64 ? 64 : 128;
+    const int64_t row = kv_type == B200FA_TYPE_Q8_0 ? Dp / kQ8BlockElems * kQ8BlockBytes : ne00 * 2;
+    Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, row, row * ne11, row * ne11 * ne12, row, row * ne11, row * ne11 * ne12,
+             (const void*)256, (const void*)256, 0, ne11, ne00, ne13};
+    int kv_div = virtual_head_split(ne01, ne02, ne12, ne03);
+    if (kv_div > 1) {
+        Shape sv = sh;
+        sv.n_head_kv = ne12 * kv_div;
+        if (stream_eligible(sv, false)) sh = sv; else kv_div = 1;
+    }
+    const Plan pl = make_plan(sh, flags, sm_count, false, false);
+    memset(out, 0, sizeof(*out));
+    out->kind = pl.kind == kPrefill ? B200FA_PLAN_PREFILL : (pl.kind == kStream ? B200FA_PLAN_STREAM : B200FA_PLAN_ROWS16);
+    out->kv_div = pl.kind == kStream ? kv_div : 1;
+    out->n_splits = pl.kind == kStream ? 1 : pl.n_splits;
+    out->grid = pl.kind == kStream ? pl.grid : 0;
+    out->cluster_k = pl.kind == kStream ? pl.cluster_k : 0;
+    out->kv_f16_copy_bytes = (int64_t)pl.kvf16_bytes;
+    out->workspace_bytes = (int64_t)pl.total;
+    return B200FA_OK;
+}
+
 int b200fa_flash_attn_ext2(const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
                            int q_type, int kv_type, int dst_type,
                            int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,

@@ -251,6 +251,21 @@ int b200fa_tensor_file_info(const char* path, b200fa_tensor_info* info);
 int b200fa_tensor_file_read(const char* path, void* dst, size_t dst_bytes);
 int b200fa_tensor_file_write(const char* path, const char* name, int type, int n_dims, const int64_t* ne, const void* data);
 
+/*
+ * Planning query (host only, no device needed): what b200fa_flash_attn_ext would do for a shape on a GPU with `sm_count` SMs —
+ * kernel family, virtual KV heads per real one (GQA bursts), KV splits (16-row kernel: splits across CTAs; tile kernel: split-KV
+ * prefill segments), stream-K grid and cluster size, bytes of f16 copies made of a q8_0 cache, workspace bytes of this plan.
+ */
+#define B200FA_PLAN_PREFILL 0 /* tcgen05 tile kernel */
+#define B200FA_PLAN_STREAM 1  /* stream-K decode kernel */
+#define B200FA_PLAN_ROWS16 2  /* register-streaming kernel over 16-row groups */
+typedef struct b200fa_plan_info {
+    int32_t kind, kv_div, n_splits, grid, cluster_k, reserved;
+    int64_t kv_f16_copy_bytes, workspace_bytes;
+} b200fa_plan_info;
+int b200fa_plan(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03, int64_t ne11, int64_t ne12,
+                int64_t ne13, uint32_t flags, int sm_count, b200fa_plan_info* out);
+
 /* Diagnostics: name of the kernel family the last b200fa_flash_attn_ext call on this thread dispatched to
  * ("decode_splitkv", "prefill_tcgen05", "rows16_mma"), and how many kernels it launched. */
 const char* b200fa_last_dispatch(void);
