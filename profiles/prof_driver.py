@@ -2,7 +2,7 @@
 """Small driver for ncu captures: runs one named workload a few times through the C ABI on plain streams
 (no CUDA graphs, no torch.distributed) so every kernel shows up as its own launch.
 
-  python profiles/prof_driver.py c2|c3|c3mask|c4|c5 [iters]
+  python profiles/prof_driver.py c2|c3|c3mask|c4|c5|chunk [iters]
 """
 import os
 import sys
@@ -58,6 +58,12 @@ def main():
         dst = torch.empty((1, 1, Hq, D), device=dev)
         ws = P.Workspace(P.workspace_size(0, 8, D, 1, Hq, 1, n_kv, Hk, 1))
         step = lambda i: P.flash_attn_ext(q, kq, vq, None, dst=dst, workspace=ws)  # noqa: E731
+    elif wl == "chunk":  # chunked prefill: 256 new queries against a 32K f16 cache (split-KV prefill + combine)
+        n_q, n_kv, H = 256, 32768, 32
+        q, k, v = rnd((1, H, n_q, D), 1), rnd((1, H, n_kv, D), 2), rnd((1, H, n_kv, D), 3)
+        dst = torch.empty((1, n_q, H, D), device=dev)
+        ws = P.Workspace(P.workspace_size(1, 1, D, n_q, H, 1, n_kv, H, 1))
+        step = lambda i: P.flash_attn_ext(q, k, v, None, dst=dst, flags=P.FLAG_WORKSPACE_ZEROED, workspace=ws)  # noqa: E731
     else:
         raise SystemExit("unknown workload " + wl)
     for i in range(iters):
