@@ -193,3 +193,32 @@ def test_merge_partials_ignores_empty_parts():
     O = np.ones((3, 4), np.float32); O[1] = 7.0
     got = oracle.merge_partials(np.array([0.0, -np.inf, 0.0]), np.array([1.0, 0.0, 1.0]), O)
     np.testing.assert_allclose(got, np.ones(4), atol=1e-7)
+
+
+@pytest.mark.parametrize("n_head,max_bias,softcap", [(6, 8.0, 0.0), (12, 4.0, 0.0), (8, 0.0, 30.0), (5, 2.5, 1.5)])
+def test_score_modifiers_against_numpy(n_head, max_bias, softcap):
+    """oracle_flash_attn_ext2 (ALiBi slopes + logit soft-cap, upstream ggml semantics — not in the reference) against an independent
+    float64 numpy evaluation of the published formulae; 6, 12 and 5 heads exercise both branches of the slope rule."""
+    D, n_q, n_kv = 32, 5, 40
+    rs = np.random.RandomState(3)
+    Q = rs.uniform(-1, 1, (1, n_head, n_q, D)).astype(np.float32)
+    K = rs.uniform(-1, 1, (1, n_head, n_kv, D)).astype(np.float16)
+    V = rs.uniform(-1, 1, (1, n_head, n_kv, D)).astype(np.float16)
+    qi = np.arange(n_q)[:, None] + (n_kv - n_q); kj = np.arange(n_kv)[None, :]
+    M = (-np.abs(qi - kj)).astype(np.float32); M[kj > qi] = -np.inf
+    M = M.astype(np.float16)
+    scale = 0.4
+    got = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), oracle.view_of(M), scale,
+                                max_bias=max_bias, logit_softcap=softcap)
+    n2 = 2 ** int(np.floor(np.log2(n_head)))
+    m0, m1 = 2.0 ** (-max_bias / n2), 2.0 ** (-(max_bias / 2.0) / n2)
+    ref = np.zeros((1, n_q, n_head, D))
+    for h in range(n_head):
+        slope = 1.0 if max_bias <= 0 else (m0 ** (h + 1) if h < n2 else m1 ** (2 * (h - n2) + 1))
+        s = Q[0, h].astype(np.float64) @ K[0, h].astype(np.float64).T * (scale / softcap if softcap else scale)
+        if softcap:
+            s = softcap * np.tanh(s)
+        s = s + slope * M.astype(np.float64)
+        p = np.exp(s - s.max(axis=1, keepdims=True)); p /= p.sum(axis=1, keepdims=True)
+        ref[0, :, h, :] = p @ V[0, h].astype(np.float64)
+    assert np.abs(got - ref).max() < 2e-6
