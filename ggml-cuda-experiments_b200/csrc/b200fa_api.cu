@@ -96,11 +96,11 @@ bool stream_eligible(const Shape& sh, bool sizing) {
     return (((uintptr_t)sh.k | (uintptr_t)sh.v | (uintptr_t)sh.nb12 | (uintptr_t)sh.nb13 | (uintptr_t)sh.nb22 | (uintptr_t)sh.nb23) % 16) == 0;
 }
 
-// How many virtual KV heads a real one is split into so that a 17..64-row GQA burst fits the stream kernel's 16 rows (1 = no split)
+// How many virtual KV heads a real one is split into so that a 17..128-row GQA burst fits the stream kernel's 16 rows (1 = no split)
 int virtual_head_split(int64_t n_q, int64_t n_head, int64_t n_head_kv, int64_t n_batch) {
     static const bool no_vh = getenv("B200FA_NO_VIRTUAL_HEADS") != nullptr;
     const int64_t gqa = n_head / n_head_kv, rows = n_q * gqa;
-    if (no_vh || rows <= 16 || rows > 64 || n_q > 16 || n_head_kv * n_batch * 8 > 65536) return 1;
+    if (no_vh || rows <= 16 || rows > 128 || n_q > 16 || n_head_kv * n_batch * 8 > 65536) return 1;
     for (int dv = 2; dv <= gqa; dv++)
         if (gqa % dv == 0 && n_q * (gqa / dv) <= 16) return dv;
     return 1;
@@ -459,7 +459,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
     Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
     sh.ext = max_bias > 0.f || softcap != 0.f;
-    // 17..64 rows per KV head from a GQA group (a burst of up to 16 query positions, e.g. speculative decoding): split every real
+    // 17..128 rows per KV head from a GQA group (a burst of up to 16 query positions, e.g. speculative decoding): split every real
     // KV head into kv_div VIRTUAL heads of gqa / kv_div q heads each, so that a unit has <= 16 rows and the stream kernel applies.
     // K/V are streamed kv_div times, but by CTAs working side by side: the repeats are L2 hits (8 positions x GQA 4, batch 8,
     // KV 8192: 190 us on the 16-row-group fallback -> 134 us).

@@ -31,7 +31,7 @@ struct FaParams {
     int Dr;            // the real head size ne00 (multiple of 8, <= D): extent of Q/K/V/dst rows in memory
     int n_kv, n_head_kv, n_batch_kv;
     int gqa;           // rk2 = n_head / n_head_kv   (flash-llama.h:128)
-    int kv_div;        // stream decode with 17..64 rows per KV head: n_head_kv and gqa describe VIRTUAL kv heads (a real head split into
+    int kv_div;        // stream decode with 17..128 rows per KV head: n_head_kv and gqa describe VIRTUAL kv heads (a real head split into
                        // kv_div groups of q heads, <= 16 rows each); K/V of virtual head v are those of real head v / kv_div.  1 otherwise
     int rk3;           // n_batch / n_batch_kv       (flash-llama.h:129)
     int64_t nb01, nb02, nb03;

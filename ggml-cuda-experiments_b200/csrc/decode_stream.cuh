@@ -3,7 +3,7 @@
 //
 // Replaces the reference's flash_attn_row<128,8,2,256> / flash_attn_row_fast (flash_row_float.h:4-413) AND
 // its fa_reduce<128,nw> (flash_row_float.h:415-472) for every call with n_q * (n_head / n_head_kv) <= 16 rows
-// per KV head (single-token decode of MHA/GQA models, short speculative bursts); GQA bursts of 17..64 rows run as virtual KV
+// per KV head (single-token decode of MHA/GQA models, short speculative bursts); GQA bursts of 17..128 rows run as virtual KV
 // heads of <= 16 rows (FaParams::kv_div).
 //
 // Work decomposition ("stream-K"): a *unit* is one (kv head, batch) pair; its keys are cut into 64-key

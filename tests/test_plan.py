@@ -38,7 +38,9 @@ def test_dispatch_boundaries():
     assert b.kind == p.PLAN_STREAM and b.kv_div == 2
     b = plan(F32, F16, 128, 5, 16, 1, 3000, 2)                                    # 5 x GQA 8 = 40 rows -> 4 virtual heads of 10 rows
     assert b.kind == p.PLAN_STREAM and b.kv_div == 4
-    assert plan(F32, F16, 128, 16, 16, 1, 4096, 2).kind == p.PLAN_ROWS16          # 128 rows from 16 positions: the 16-row kernel
+    b = plan(F32, F16, 128, 16, 16, 1, 4096, 2)                                   # 16 x GQA 8 = 128 rows -> 8 virtual heads of 16 rows
+    assert b.kind == p.PLAN_STREAM and b.kv_div == 8
+    assert plan(F32, F16, 128, 16, 32, 1, 4096, 2).kind == p.PLAN_ROWS16          # 256 rows from 16 positions: the 16-row kernel
     assert plan(F32, F16, 128, 17, 8, 1, 4096, 8).kind == p.PLAN_PREFILL          # more than 16 positions: the tile kernel
     assert plan(F32, F16, 128, 17, 8, 1, 4096, 8, flags=2).kind == p.PLAN_ROWS16  # ... unless B200FA_FLAG_NO_TCGEN05
     assert plan(F32, F16, 80, 1, 8, 1, 1000, 8).kind == p.PLAN_STREAM             # padded head sizes
