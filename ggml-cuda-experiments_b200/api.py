@@ -28,7 +28,8 @@ def lib() -> C.CDLL:
     """Load libb200fa.so (building it if the sources are newer).  Fails loudly if it cannot be had."""
     global _lib
     if _lib is None:
-        path = LIB if os.path.exists(LIB) and os.environ.get("B200FA_NO_REBUILD") else build()
+        # B200FA_LIB: a tuning build of the same sources (profiles/ tools compare variants in one GPU call)
+        path = os.environ.get("B200FA_LIB") or (LIB if os.path.exists(LIB) and os.environ.get("B200FA_NO_REBUILD") else build())
         l = C.CDLL(path)
         i64, vp = C.c_int64, C.c_void_p
         l.b200fa_status_string.restype = C.c_char_p

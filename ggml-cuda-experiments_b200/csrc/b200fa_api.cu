@@ -87,6 +87,8 @@ bool stream_eligible(const Shape& sh, bool sizing) {
     const int64_t rows = sh.n_q * (sh.n_head / sh.n_head_kv);
     if (rows > 16 || (sh.D != 64 && sh.D != 128)) return false;
     if (sh.n_head_kv * sh.n_batch > 65536) return false;
+    // the kernel's chunk bookkeeping is 32-bit (DK_MAX_TOTAL_X_GRID): out of reach for any K/V a 180 GB device holds, D = 64 q8_0 aside
+    if (sh.n_head_kv * sh.n_batch * ((sh.n_kv + DK_CHUNK - 1) / DK_CHUNK) * (DK_TAB + 1) > DK_MAX_TOTAL_X_GRID) return false;
     static const bool off = getenv("B200FA_DECODE_IMPL") && !strcmp(getenv("B200FA_DECODE_IMPL"), "rows16");
     if (off) return false;
     if (sizing || sh.kv_type == B200FA_TYPE_F16) return true;
@@ -308,14 +310,14 @@ int launch_combine(const float* part, int n_parts, int64_t rows, void* dst, int 
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
-template <int D, int KV, int RH, bool EXT>
+template <int D, int KV, int RH, bool EXT, bool T8 = false>
 int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t st) {
-    constexpr int smem = dk_smem_bytes<D, KV == B200FA_TYPE_Q8_0, RH>();
+    constexpr int smem = dk_smem_bytes<D, KV == B200FA_TYPE_Q8_0, RH, T8>();
     static thread_local bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
+        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT, T8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev] = true;
     }
     // Programmatic dependent launch: this kernel may be scheduled while the previous kernel of the stream drains (it waits in-kernel,
@@ -323,7 +325,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
     static const bool no_pdl = getenv("B200FA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && a.peers == nullptr;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(dk_threads<T8>()); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
     if (a.cluster_k > 1) {
@@ -337,7 +339,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         na++;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT, T8>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
@@ -347,6 +349,10 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     a.rec = reinterpret_cast<float*>(ws + pl.ctr_bytes);
     a.timeline = g_timeline;
     a.cluster_k = pl.cluster_k;
+    // every CTA's run lies inside one unit (unit-aligned grid, or one chunk per CTA): the fold follows the CTA's last chunk, the deep ring applies
+    a.deep_ring = (pl.grid > 0 && pl.n_units > 0 && pl.grid % pl.n_units == 0 && pl.total_chunks >= pl.grid) ? 1 : 0;
+    { static const bool nd = getenv("B200FA_NO_DEEP_RING") != nullptr; if (nd) a.deep_ring = 0; }
+    { static const int rg = getenv("B200FA_RING") ? atoi(getenv("B200FA_RING")) : 0; a.ring = rg; }
     a.peers = g_seqpar.peers; a.rank = g_seqpar.rank; a.world = g_seqpar.world; a.fdst = g_seqpar.fdst; a.fdst_type = g_seqpar.fdst_type;
     a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
     { static const bool nb = getenv("B200FA_NO_MASK_BULK") != nullptr; if (nb) a.mask_bulk = 0; }
@@ -373,8 +379,13 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
 #define B200FA_STREAM_E(DD, KK, EE) (small ? launch_stream_t<DD, KK, 1, EE>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2, EE>(p, a, pl.grid, tk, tv, st))
 #define B200FA_STREAM(DD, KK) (ext ? B200FA_STREAM_E(DD, KK, true) : B200FA_STREAM_E(DD, KK, false))
+#define B200FA_STREAM_T8(DD) (ext ? launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, true, true>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, false, true>(p, a, pl.grid, tk, tv, st))
+    // q8_0 units of at most 8 rows: the transposed tile (decode_stream.cuh, T8)
+    static const bool q8_rowmajor = getenv("B200FA_Q8_ROWMAJOR") != nullptr;
+    if (q8 && small && !q8_rowmajor) return p.D == 128 ? B200FA_STREAM_T8(128) : B200FA_STREAM_T8(64);
     if (p.D == 128) return q8 ? B200FA_STREAM(128, B200FA_TYPE_Q8_0) : B200FA_STREAM(128, B200FA_TYPE_F16);
     return q8 ? B200FA_STREAM(64, B200FA_TYPE_Q8_0) : B200FA_STREAM(64, B200FA_TYPE_F16);
+#undef B200FA_STREAM_T8
 #undef B200FA_STREAM
 #undef B200FA_STREAM_E
 }

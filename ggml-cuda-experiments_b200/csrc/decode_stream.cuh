@@ -34,46 +34,78 @@
 
 namespace b200fa {
 
+// Diagnostics are compiled in only with -DB200FA_TUNING (profiles/timeline.py builds its own copy of the library): per-CTA and
+// per-chunk %globaltimer stamps, and "stream but skip the tile maths" (FaParams::dbg_mode).
+#ifdef B200FA_TUNING
+#define DK_TL(cond, idx, val) do { if (a.timeline != nullptr && (cond)) a.timeline[idx] = (val); } while (0)
+#define DK_DBG_SKIP_MATH (p.dbg_mode == 1)
+#else
+#define DK_TL(cond, idx, val) do { } while (0)
+#define DK_DBG_SKIP_MATH false
+#endif
+
 constexpr int DK_CHUNK = 64;   // keys per pipeline stage
-constexpr int DK_CWARPS = 8;   // consumer warps (two groups of four)
 constexpr int DK_PWARPS = 4;   // producer warps: K box 0 | K box 1 | V box 0 | V box 1 + mask rows (q8_0: K | - | V | mask)
-constexpr int DK_THREADS = (DK_CWARPS + DK_PWARPS) * 32;
-constexpr int DK_SLOTS = DK_CWARPS;  // cross-warp merge slots: one per consumer warp
-constexpr int DK_MASK_BYTES = 16 * 128;
+// consumer warps: groups of four (one 16-key tile of a chunk each).  T8 (the transposed q8_0 tile, below): three groups.
+template <bool T8> __host__ __device__ constexpr int dk_cwarps() { return T8 ? 12 : 8; }
+template <bool T8> __host__ __device__ constexpr int dk_threads() { return (dk_cwarps<T8>() + DK_PWARPS) * 32; }
 constexpr int DK_REC_ROWS = 16;
 constexpr int DK_REC_PAD = 4;     // record rows are D + 4 floats (16-byte aligned): O~[D], m, l, 2 unused
 
-template <int D, bool Q8>
+template <int D, bool Q8, bool T8 = false>
 struct DkGeom {
     static constexpr int kRowBytes = Q8 ? D / 32 * kQ8BlockBytes : D * 2;
     static constexpr int kBoxes = D / 64;                                    // 64-dim TMA boxes per K (or V) chunk
     static constexpr int kKBytes = Q8 ? DK_CHUNK * kRowBytes : kBoxes * 8192;  // bytes of K (== V) per stage
     static constexpr int kVOff = kKBytes;
     static constexpr int kMaskOff = 2 * kKBytes;
-    static constexpr int kStageBytes = (2 * kKBytes + DK_MASK_BYTES + (Q8 ? 16 : 0) + 1023) / 1024 * 1024;
+    static constexpr int kMaskBytes = (T8 ? 8 : 16) * 128;                   // one 128-byte line per query position
+    // q8_0: fragment loads are whole aligned words around a 2-byte-aligned payload, so the last row may be over-read by
+    // up to 8 bytes: into V, into the mask lines, and after those into 16 bytes of padding
+    static constexpr int kStageBytes = (2 * kKBytes + kMaskBytes + (Q8 ? 16 : 0) + 1023) / 1024 * 1024;
 };
-template <int D, int RH>
+template <int D, int RH, bool T8 = false>
 struct DkMerge {
-    static constexpr int kFloatsPerLane = (D / 8) * 2 * RH + 2 * RH;  // O fragment + (m, l) per live row half
+    // floats a lane parks per fold: its O fragment + (m, l) per live row (T8: O^T tiles + rows 2t, 2t+1)
+    static constexpr int kFloatsPerLane = T8 ? (D / 16) * 4 + 4 : (D / 8) * 2 * RH + 2 * RH;
     static constexpr int kSlotBytes = kFloatsPerLane * 32 * 4;
-    static constexpr int kBytes = DK_SLOTS * kSlotBytes;
+    static constexpr int kBytes = dk_cwarps<T8>() * kSlotBytes;
 };
 constexpr int DK_TL_CHUNK0 = 160 * 8;  // diagnostics: per-chunk stamps of CTA 0 start here (4 per chunk, first 512 chunks)
 constexpr int DK_TAB = 160;           // contributor table entries (>= SM count)
-constexpr int DK_TAIL_BYTES = 2 * 8 * 8 + 64 + DK_TAB * 4;  // barriers, flag, table
+constexpr int DK_TAIL_BYTES = 2 * 16 * 8 + 64 + DK_TAB * 4;  // barriers (up to 16 full + 16 empty), flag, table
 constexpr int DK_SMEM_LIMIT = 227 * 1024;
-template <int D, bool Q8, int RH>
+template <int D, bool Q8, int RH, bool T8 = false>
 __host__ __device__ constexpr int dk_stages() {
-    // As deep a ring as fits beside the merge slots, at most 8 — and EVEN: chunk j is consumed by warp group j & 1, and a
-    // stage must always be consumed by the same group, because an mbarrier waiter may never skip a phase (a group that
-    // only saw every other phase of a stage could find its parity already satisfied by the phase before).
-    int n = (DK_SMEM_LIMIT - 1024 - DK_TAIL_BYTES - DkMerge<D, RH>::kBytes) / DkGeom<D, Q8>::kStageBytes;
-    n = n > 8 ? 8 : n;
-    return n & ~1;
+    // As deep a ring as fits beside the merge slots, at most 8 (T8: 9) — and a MULTIPLE OF THE GROUP COUNT: chunk j is consumed by
+    // warp group j % groups, and a stage must always be consumed by the same group, because an mbarrier waiter may never skip a
+    // phase (a group that only saw every other phase of a stage could find its parity already satisfied by the phase before).
+    constexpr int groups = dk_cwarps<T8>() / 4;
+    int n = (DK_SMEM_LIMIT - 1024 - DK_TAIL_BYTES - DkMerge<D, RH, T8>::kBytes) / DkGeom<D, Q8, T8>::kStageBytes;
+    n = n > (T8 ? 9 : 8) ? (T8 ? 9 : 8) : n;
+    return n / groups * groups;
 }
-template <int D, bool Q8, int RH>
+// The DEEP ring: when every CTA's run is a single unit segment (unit-aligned grids: the few-unit shapes, where bytes in flight per SM
+// are what bounds the stream), the fold only starts after the CTA's last chunk has been consumed, so the merge slots may alias the
+// tail of the ring: the ring takes the whole shared memory.  Multi-segment runs (stream-K over many units) fold in mid-stream and
+// keep the ring and the slots apart (dk_stages).  The depth is a kernel argument (DkArgs::ring); slots always start at stage dk_stages().
+template <int D, bool Q8, int RH, bool T8 = false>
+__host__ __device__ constexpr int dk_stages_deep() {
+    constexpr int groups = dk_cwarps<T8>() / 4;
+    int n = (DK_SMEM_LIMIT - 1024 - DK_TAIL_BYTES) / DkGeom<D, Q8, T8>::kStageBytes;
+    n = n > 12 ? 12 : n;
+    n = n / groups * groups;
+    return n < dk_stages<D, Q8, RH, T8>() ? dk_stages<D, Q8, RH, T8>() : n;
+}
+template <int D, bool Q8, int RH, bool T8 = false>
+__host__ __device__ constexpr int dk_ring_bytes() {  // ring + merge slots (aliased or not), whichever ends later
+    constexpr int safe = dk_stages<D, Q8, RH, T8>() * DkGeom<D, Q8, T8>::kStageBytes + DkMerge<D, RH, T8>::kBytes;
+    constexpr int deep = dk_stages_deep<D, Q8, RH, T8>() * DkGeom<D, Q8, T8>::kStageBytes;
+    return safe > deep ? safe : deep;
+}
+template <int D, bool Q8, int RH, bool T8 = false>
 __host__ __device__ constexpr int dk_smem_bytes() {
-    return dk_stages<D, Q8, RH>() * DkGeom<D, Q8>::kStageBytes + DkMerge<D, RH>::kBytes + DK_TAIL_BYTES + 1024;
+    return dk_ring_bytes<D, Q8, RH, T8>() + DK_TAIL_BYTES + 1024;
 }
 
 struct DkArgs {
@@ -95,6 +127,8 @@ struct DkArgs {
     int q8_lines;            // q8_0: whole 128-byte lines per head covered by the [lines][128 B] tensor maps (0 = 1-D bulk copies only)
     int cluster_k;           // > 1: the grid is launched in clusters of cluster_k CTAs = the CTAs of one unit; their records are
                              // merged through distributed shared memory (no global fence / atomic / L2 round trips)
+    int deep_ring;           // every CTA's run is one unit segment: the ring may use up to dk_stages_deep stages
+    int ring;                // tuning (B200FA_TUNING builds): ring depth to use, 0 = the default for the mode
 };
 __device__ __forceinline__ unsigned long long dk_now() {
     unsigned long long t;
@@ -122,11 +156,25 @@ __device__ __forceinline__ uint2 lds_u8x8(uint32_t a) {
     const uint32_t w0 = lds32(base), w1 = lds32(base + 4), w2 = lds32(base + 8);
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(DK_CWARPS * 32) : "memory"); }
-
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+template <int CW>
+__device__ __forceinline__ void bar_consumers_n() { asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory"); }
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+    uint32_t r;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
 }
+// D = A * B + C with C in its own registers (the QK accumulator of the transposed q8_0 tile starts at -1152 * sum(Q))
+__device__ __forceinline__ void mma_16816_c(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
+                                            float c0, float c1, float c2, float c3) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
 // address of `local` (a shared-memory address of this CTA) in the shared memory of CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t cluster_map(uint32_t local, uint32_t rank) {
     uint32_t r;
@@ -136,20 +184,36 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 // owner CTA of flat chunk x when CTA c covers [c*T/G, (c+1)*T/G)
-__device__ __forceinline__ long long dk_owner(long long x, long long T, long long G) { return ((x + 1) * G - 1) / T; }
+// (32-bit arithmetic throughout: the host only plans this kernel when total * (grid + 1) < 2^31 — DK_MAX_TOTAL_X_GRID — which every
+// K/V that fits a 180 GB device satisfies except D = 64 q8_0 caches beyond 125 GB; 64-bit divisions are subroutine calls, and
+// five of them in the prologue were most of a microsecond)
+__device__ __forceinline__ unsigned dk_owner(unsigned x, unsigned T, unsigned G) { return ((x + 1u) * G - 1u) / T; }
+constexpr long long DK_MAX_TOTAL_X_GRID = 0x7fffffffLL;
 
 // EXT: the ext2 score modifiers (ALiBi slope on the mask, tanh soft-cap) are compiled in; the plain entry never pays for them
-template <int D, int KV_TYPE, int RH, bool EXT = false>
-__global__ void __launch_bounds__(DK_THREADS, 1)
+// T8: the transposed q8_0 tile for units of at most 8 rows (S^T = K Q^T, O^T += V^T P'^T: the quantised rows are the A operands,
+// N = 8 covers all live rows, half the MMAs and half the accumulator registers of the row-major tile; see the T8 block below and
+// tests/test_q8t_layout.py, which restates its register algebra lane by lane on the CPU).
+template <int D, int KV_TYPE, int RH, bool EXT = false, bool T8 = false>
+__global__ void __launch_bounds__(dk_threads<T8>(), 1)
 fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkArgs a,
                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV) {
     using namespace ptx;
     static_assert(D == 64 || D == 128, "head size");
     constexpr bool Q8 = (KV_TYPE == B200FA_TYPE_Q8_0);
-    using Geo = DkGeom<D, Q8>;
-    using Mrg = DkMerge<D, RH>;
-    constexpr int NS = dk_stages<D, Q8, RH>();
-    static_assert(NS >= 4 && NS % 2 == 0, "ring must be even (see dk_stages) and at least 4 deep");
+    static_assert(!T8 || (Q8 && RH == 1), "the transposed tile is the q8_0 kernel for <= 8 rows");
+    using Geo = DkGeom<D, Q8, T8>;
+    using Mrg = DkMerge<D, RH, T8>;
+    constexpr int CW = dk_cwarps<T8>();  // consumer warps
+    constexpr int NG = CW / 4;           // consumer groups: chunk j belongs to group j % NG
+    constexpr int NS_SAFE = dk_stages<D, Q8, RH, T8>(), NS_DEEP = dk_stages_deep<D, Q8, RH, T8>();
+    static_assert(NS_SAFE >= 3 && NS_SAFE % NG == 0 && NS_DEEP % NG == 0 && NS_DEEP <= 16, "ring depth must be a multiple of the group count (see dk_stages)");
+#ifdef B200FA_TUNING
+    const int NS = a.ring > 0 ? min(a.ring / NG * NG, a.deep_ring ? NS_DEEP : NS_SAFE) : (a.deep_ring ? NS_DEEP : NS_SAFE);
+#else
+    const int NS = a.deep_ring ? NS_DEEP : NS_SAFE;
+#endif
+    auto bar_consumers = []() { bar_consumers_n<CW>(); };
     constexpr int NC4 = D / 32;  // 16-byte chunks per lane per K row == q8_0 blocks per row
     constexpr int NCV = D / 64;  // 64-wide halves of a V row
     constexpr int NT = D / 8;    // output n-tiles
@@ -159,57 +223,90 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     extern __shared__ uint8_t dk_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dk_smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t stages_u32 = smem_u32(smem);
-    float* merge = reinterpret_cast<float*>(smem + NS * Geo::kStageBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Geo::kStageBytes + Mrg::kBytes);
-    uint64_t* empty = full + 8;
-    int* s_flag = reinterpret_cast<int*>(empty + 8);
+    float* merge = reinterpret_cast<float*>(smem + NS_SAFE * Geo::kStageBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + dk_ring_bytes<D, Q8, RH, T8>());
+    uint64_t* empty = full + 16;
+    int* s_flag = reinterpret_cast<int*>(empty + 16);
     int* s_tab = s_flag + 16;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long G = gridDim.x;
-    const long long start = (long long)blockIdx.x * a.total / G, stop = ((long long)blockIdx.x + 1) * a.total / G;
+    const unsigned G = gridDim.x, total = (unsigned)a.total;
+    const unsigned start = blockIdx.x * total / G, stop = (blockIdx.x + 1u) * total / G;
     const int my_chunks = (int)(stop - start);
     // Programmatic dependent launch (the host opts in per launch): the NEXT kernel of the stream may be scheduled onto SMs as this
     // grid's CTAs retire, and runs its prologue there; every thread of this kernel in turn waits (griddepcontrol.wait, below) for
     // the previous grid to have completed and flushed before it touches global memory.  Both are no-ops on a plain launch.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 7, dk_now());  // kernel entry
+    if (warp == 0 && my_chunks > 0) {
+        // Ask L2 for the Q rows of the CTA's first unit before anything else happens.  Once the producers' opening burst (the
+        // whole ring: 20-30 MB over the chip) is queued in DRAM, a Q line that misses L2 comes back BEHIND it — measured 3-7 us
+        // after kernel entry, with landed stages waiting for their consumers all that time.  (L2 is the coherence point, so
+        // a prefetch ahead of griddepcontrol.wait is harmless.)
+        const int u0 = (int)(start / (unsigned)a.cph), ik2_0 = u0 % p.n_head_kv, iq3_0 = u0 / p.n_head_kv;
+        const int row_bytes = p.Dr * (p.q_type == B200FA_TYPE_F16 ? 2 : 4);
+        for (int R = lane >> 2; R < p.n_q * p.gqa; R += 8) {
+            const char* qrow = p.q + (int64_t)(R / p.gqa) * p.nb01 + (int64_t)(ik2_0 * p.gqa + R % p.gqa) * p.nb02 + (int64_t)iq3_0 * p.nb03;
+            if ((lane & 3) * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(qrow + (lane & 3) * 128));
+        }
+    }
 
-    if (warp >= DK_CWARPS) {
+    if (warp >= CW) {
         // ===================== producers =====================
         // Every TMA / bulk operation costs its issuing thread ~90 ns (measured: +10 us on the C5 shape for one extra 128-byte copy
         // per chunk): a single issuer (5 operations per f16 chunk) was a bottleneck of the stream.  Four warps issue side by side,
         // one operation each: K box 0 | K box 1 | V box 0 | V box 1 and the mask rows (q8_0: K | nothing | V | mask rows); each
         // arms the chunk's barrier with its own byte count.  (Lanes of ONE warp issuing side by side measured slower.)
-        const int which = warp - DK_CWARPS;
-        const bool isV = which >= 2;   // warps 8, 9: K;  10, 11: V
-        const int box = which & 1;      // f16: the 64-dim box of the row this warp loads; q8_0: only box 0 exists
+        // q8_0 has one operation per tensor and chunk, and chunks of half the bytes: the four warps are K even chunks | K odd chunks |
+        // V even | V odd (each K warp also copies its chunk's mask rows), so an issuing thread has two chunk periods per iteration.
+        const int which = warp - CW;
+        const bool isV = which >= 2;   // first two producer warps: K;  last two: V
+        const int box = Q8 ? 0 : (which & 1);   // f16: the 64-dim box of the row this warp loads
+        constexpr int PSTRIDE = Q8 ? 2 : 1;     // chunks between two issues of one producer
+        constexpr int FULL_ARRIVALS = Q8 ? 2 : DK_PWARPS;  // producers that arm a chunk's barrier
+        const int pfirst = Q8 ? (which & 1) : 0;
         if (which == 0 && lane == 0) {
-            for (int s = 0; s < NS; s++) { mbar_init(&full[s], DK_PWARPS); mbar_init(&empty[s], 4); }
+            for (int s = 0; s < NS_DEEP; s++) { mbar_init(&full[s], FULL_ARRIVALS); mbar_init(&empty[s], 4); }
             fence_barrier_init();
         }
         if (lane == 0 && (!Q8 || a.q8_lines > 0)) prefetch_tensormap(isV ? &tmV : &tmK);
         asm volatile("bar.sync 2, %0;" ::"n"(DK_PWARPS * 32) : "memory");  // the barriers exist before the other producers touch them
+        asm volatile("bar.arrive 3, %0;" ::"n"(dk_threads<T8>()) : "memory");  // ... and tell the consumers so, without waiting for them
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        int pu = (int)(start / a.cph), pch = (int)(start - (long long)pu * a.cph);  // unit / chunk of the next issue
-        auto issue = [&](int i) {
-            const int u = pu, ch = pch;
-            if (++pch == a.cph) { pch = 0; pu++; }
-            const int iq3 = u / p.n_head_kv, ik3 = iq3 / p.rk3;
-            const int ik2 = (u % p.n_head_kv) / p.kv_div;  // the REAL kv head whose K/V this (possibly virtual) unit streams
+        // The per-chunk path of an issuing thread is short on purpose: one thread runs it serially for every chunk of the CTA, and a
+        // chunk lasts ~400 ns at the HBM rate (q8_0).  Everything that depends only on the unit (integer divisions by run-time values:
+        // ~150 dependent instructions, which used to cost ~400 ns per chunk and bounded the q8_0 stream at 4.5 TB/s) is recomputed
+        // only when the run crosses into the next unit.
+        int pu = (int)((start + pfirst) / (unsigned)a.cph), pch = (int)(start + pfirst - (unsigned)pu * (unsigned)a.cph);  // unit / chunk of the next issue
+        int ik2 = 0, ik3 = 0;  // the REAL kv head / kv batch whose K/V the (possibly virtual) unit pu streams
+        auto set_unit = [&](int u) {
+            const int iq3 = u / p.n_head_kv;
+            ik3 = iq3 / p.rk3;
+            ik2 = (u - iq3 * p.n_head_kv) / p.kv_div;
+        };
+        set_unit(pu);
+        const int q8_box_chunks = (Q8 && a.q8_lines > 0) ? (int)(((int64_t)a.q8_lines * 128) / Geo::kKBytes) : 0;  // chunks of a head inside the line maps
+        const int whole_chunks = p.n_kv / DK_CHUNK;                                        // chunks with all 64 keys
+        const int mrows_full = ((Q8 ? !isV : which == DK_PWARPS - 1) && a.mask_bulk) ? p.n_q : 0;
+        const CUtensorMap* tm = isV ? &tmV : &tmK;
+        const bool has_box = box < Geo::kBoxes;                  // (D = 64, f16: one box per tensor)
+        const uint32_t half_off = isV ? Geo::kVOff : 0;          // this producer's half of a stage
+        int pstage = pfirst % NS, pphase = 1;  // stage of the next issue; parity of its `empty` barrier that means "free" (first lap: free at once)
+        auto issue = [&]() {
+            const int ch = pch;
             const int key0 = ch * DK_CHUNK;
-            const int stage = i % NS;
-            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes + (isV ? Geo::kVOff : 0);  // this producer's half of the stage
-            uint8_t* sp = smem + stage * Geo::kStageBytes + (isV ? Geo::kVOff : 0);
-            const bool whole = key0 + DK_CHUNK <= p.n_kv;
-            const int mrows = (which == DK_PWARPS - 1 && a.mask_bulk && whole) ? p.n_q : 0;
-            const CUtensorMap* tm = isV ? &tmV : &tmK;
-            const bool has_box = Q8 ? box == 0 : box < Geo::kBoxes;  // q8_0: one operation per tensor (warps 8 and 10)
+            const int stage = pstage;
+            pstage += PSTRIDE;
+            if (pstage >= NS) { pstage -= NS; pphase ^= 1; }
+            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes + half_off;
+            uint8_t* sp = smem + stage * Geo::kStageBytes + half_off;
+            const int mrows = ch < whole_chunks ? mrows_full : 0;
             if (!has_box) {
                 mbar_arrive_expect_tx(&full[stage], mrows * 128);
             } else if constexpr (!Q8) {
                 mbar_arrive_expect_tx(&full[stage], 8192 + mrows * 128);
                 tma_load_4d(sp + box * 8192, tm, &full[stage], 64 * box, key0, ik2, ik3);
-            } else if (a.q8_lines > 0 && (int64_t)(ch + 1) * Geo::kKBytes <= (int64_t)a.q8_lines * 128) {
+            } else if (ch < q8_box_chunks) {
                 // q8_0, chunk inside the whole-128-byte-line part of the head: the head's rows are one contiguous byte range, which
                 // the tensor maps describe as [lines][128 B] — one box of kKBytes/128 lines per K and per V chunk (a little faster
                 // than 1-D bulk copies of the same bytes: 71 vs 74-81 us of pure streaming on the C5 shape).
@@ -227,28 +324,31 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
             for (int r = 0; r < mrows; r++)
                 bulk_g2s(stages_u32 + stage * Geo::kStageBytes + Geo::kMaskOff + r * 128, p.mask + (int64_t)r * p.nb31 + (int64_t)key0 * 2, 128, &full[stage]);
+            pch += PSTRIDE;
+            if (pch >= a.cph) {
+                do { pch -= a.cph; pu++; } while (pch >= a.cph);
+                set_unit(pu);
+            }
         };
-        const bool tl = a.timeline != nullptr && blockIdx.x == 0 && which == 0;  // per-chunk diagnostics of CTA 0
-        int i = 0;
-        if (lane == 0)
-            for (; i < min(NS, my_chunks); i++) issue(i);  // the ring starts filling before anyone else is ready
-        __syncthreads();
         if (lane == 0) {
-            for (; i < my_chunks; i++) {
-                mbar_wait(&empty[i % NS], ((i / NS) & 1) ^ 1);
-                if (tl && i < 512) a.timeline[DK_TL_CHUNK0 + i * 4 + 0] = dk_now();  // stage free again
-                issue(i);
-                if (tl && i < 512) a.timeline[DK_TL_CHUNK0 + i * 4 + 1] = dk_now();  // operations issued
+            for (int i = pfirst; i < my_chunks; i += PSTRIDE) {
+                if (i >= NS) mbar_wait(&empty[pstage], pphase);  // the first lap needs no wait: the ring starts filling at once
+                DK_TL(blockIdx.x == 0 && which == 0 && i < 512, DK_TL_CHUNK0 + i * 4 + 0, dk_now());  // stage free again
+                issue();
+                DK_TL(blockIdx.x == 0 && which == 0 && i < 512, DK_TL_CHUNK0 + i * 4 + 1, dk_now());  // operations issued
             }
         }
         __syncwarp();
-        if (a.cluster_k > 1) cluster_sync_all();  // every thread of the cluster takes part in the cluster barrier
+        if (a.cluster_k > 1) { cluster_sync_all(); cluster_sync_all(); }  // every thread of the cluster takes part in both cluster barriers
         return;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    __syncthreads();
 
     // ===================== consumers =====================
+    // (They meet the producers' "mbarriers are initialised" signal, bar.sync 3, only right before their first wait on a stage: the
+    // Q rows of the first unit are requested before that.  Measured: once the producers' opening burst — the whole ring, 20-30 MB
+    // over the chip — is queued in DRAM, a Q line that misses L2 comes back BEHIND it, 3-7 us later, and the consumers sat idle
+    // on landed stages for that long.)
     const int g = lane >> 2, t = lane & 3;
     const int group = warp >> 2, sub = warp & 3;
     const int rows_total = p.n_q * p.gqa;
@@ -256,17 +356,26 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 
     // Full accumulator quads also when only fragment rows g are live (RH == 1): rows 8-15 of A are fed zeros, so entries 2-3 stay
     // what they were (zero) and the HMMA accumulates in place — no per-instruction re-zeroing or moves to build its C/D quad.
-    float o[NT][4];
-    float m_run[RH], l_run[RH];
-    uint32_t qa[NC4][RH][4];
-    int iq1r[RH], rq[RH];   // query position / q head within the GQA group of the lane's rows
-    float mslope[RH];       // log2(e) x ALiBi slope of the row's head (set per unit): the factor on raw mask values
-    bool rvalid[RH];
-    int lim[RH];
-    const char* mrow[RH];
+    // The lane's rows: fragment rows g (+ 8) of the row-major tile; accumulator columns 2t, 2t+1 of the transposed one (T8).
+    constexpr int NR = T8 ? 2 : RH;
+    constexpr int NB = D / 32;   // q8_0 blocks per row
+    constexpr int NMT = D / 16;  // T8: 16-dim m-tiles of O^T
+    float o[T8 ? 1 : NT][4];
+    float m_run[NR], l_run[NR];
+    uint32_t qa[T8 ? 1 : NC4][RH][4];
+    // T8 state: O^T tiles (c0/c1 = dim(mt, g) of rows 2t/2t+1, c2/c3 = dim(mt, g + 8)), Q as B fragments (row g, dims 32b + 8t..+7),
+    // and -1152 x the block sums of Q rows 2t, 2t+1: the C operand that cancels the bias left in the converted K bytes
+    float oT[T8 ? NMT : 1][4];
+    uint32_t qb[T8 ? NB : 1][4];
+    float qsn[T8 ? NB : 1][2];
+    int iq1r[NR], rq[NR];   // query position / q head within the GQA group of the lane's rows
+    float mslope[NR];       // log2(e) x ALiBi slope of the row's head (set per unit): the factor on raw mask values
+    bool rvalid[NR];
+    int lim[NR];
+    const char* mrow[NR];
 #pragma unroll
-    for (int h = 0; h < RH; h++) {
-        const int R = g + 8 * h;
+    for (int h = 0; h < NR; h++) {
+        const int R = T8 ? 2 * t + h : g + 8 * h;
         rvalid[h] = R < rows_total;
         iq1r[h] = (rvalid[h] ? R : 0) / p.gqa;
         rq[h] = (rvalid[h] ? R : 0) % p.gqa;
@@ -278,6 +387,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 
     // S = Q K^T (fp32) for the lane's 2 x 4 score slots
     auto qk_tile = [&](const Tile& T, float (&s)[2][4]) {
+        if constexpr (!T8) {  // the row-major tile (f16 K/V, and q8_0 units of 9-16 rows)
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
             if constexpr (Q8) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -304,9 +414,11 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 }
             }
         }
+        }
     };
     // scale, mask, online softmax (lane holds keys kv0+4t+j, j=0..3, of its rows), then O += P V
     auto softmax_pv_tile = [&](const Tile& T, const float (&s)[2][4], int kv0) {
+        if constexpr (!T8) {  // the row-major tile (f16 K/V, and q8_0 units of 9-16 rows)
         float pr[RH][4];
 #pragma unroll
         for (int h = 0; h < RH; h++) {
@@ -377,6 +489,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 mma_16816(o[c * 8 + j], pa0, pa1, pa2, pa3, b0, b1);  // RH == 1: pa1 = pa3 = 0
             }
         }
+        }
     };
 
     // Per-lane byte offsets into a stage, fixed for the whole kernel: every fragment load below is stage base + one of
@@ -410,6 +523,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 
     // fragments of one 16-key sub-tile out of a landed stage: K (+ K scales, mask) first, V once the scores are issued
     auto read_k = [&](Tile& T, uint32_t sb, int kv0, bool staged_mask) {
+        if constexpr (!T8) {  // the row-major tile (f16 K/V, and q8_0 units of 9-16 rows)
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
 #pragma unroll
@@ -448,8 +562,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 }
             }
         }
+        }
     };
     auto read_v = [&](Tile& T, uint32_t sb, int kv0) {
+        if constexpr (!T8) {  // the row-major tile (f16 K/V, and q8_0 units of 9-16 rows)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
 #pragma unroll
@@ -465,12 +581,14 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 }
             }
         }
+        }
     };
 
     // Slot layout: [k][lane] floats.  k < KO: the lane's O fragment, k = (n-tile * 2*RH + e) with e = 2h + e1, which is
     // row g + 8h, dim 64c + 16t + j + 8*e1 for n-tile c*8 + j;  k = KO + 2h / + 2h + 1: that row's m / l.
-    constexpr int KO = NT * 2 * RH, KPT = KO / DK_CWARPS;
+    constexpr int KO = T8 ? NMT * 4 : NT * 2 * RH;
     auto slot_st = [&]() {
+        if constexpr (!T8) {  // the row-major tile (f16 K/V, and q8_0 units of 9-16 rows)
         float* sp = merge + warp * (Mrg::kSlotBytes / 4) + lane;
         int k = 0;
 #pragma unroll
@@ -479,9 +597,182 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             for (int e = 0; e < 2 * RH; e++) sp[(k++) * 32] = o[n][e];
 #pragma unroll
         for (int h = 0; h < RH; h++) { sp[(k++) * 32] = m_run[h]; sp[(k++) * 32] = l_run[h]; }
+        }
     };
-    const bool stamp = a.timeline != nullptr && threadIdx.x == 0;
-    if (stamp) a.timeline[blockIdx.x * 8 + 0] = dk_now();
+
+    // ===================== the transposed q8_0 tile (T8) =====================
+    // One warp, 16 keys.  Contraction / accumulator slot s = 8h + 2t' + j of the tile is key 4t' + 2h + j, so that
+    //   * the lane's score slots g and g + 8 are keys keyA = 4(g >> 1) + (g & 1) and keyA + 2,
+    //   * after movmatrix the lane's P' fragment covers keys 4t .. 4t+3: four consecutive V rows.
+    // S^T[key][row] = sum_b dK[key][b] * (sum_{i in b} (1152 + k_i) q_i - 1152 sum_{i in b} q_i): two MMAs per 32-dim block whose
+    // A operands are the K bytes converted with ONE byte permute per pair (0x64 high bytes make 1024 + (byte ^ 0x80) = 1152 + k in
+    // f16; the subtraction the row-major tile spends an HADD2 per pair on is the accumulator's initial value here), lane t of row g
+    // taking payload bytes 8t..8t+7 of the block (the contraction index is permuted the same way in Q's B fragments).
+    // O^T[dim][row] += sum_key v[key][dim] * (p[key][row] dV[key][b]): P' = p * dV per block, rounded to f16, transposed by
+    // movmatrix into the B fragment; the A operand pairs the bytes of two consecutive keys for one dim (one permute + one logic op
+    // + the bias subtraction per pair).  m-tile mt, fragment row m is head dim 32(mt>>1) + 4(m&7) + 2(mt&1) + (m>>3).
+    // The running max is lazy: it is raised (warp-wide butterflies, O^T rescaled) only when some score exceeds it by 2^kLazy,
+    // so p <= 2^kLazy and the common tile costs one vote instead of six shuffles.
+    constexpr float kLazy = 6.f;
+    const int keyA = 4 * (g >> 1) + (g & 1);
+    const uint32_t t8_ka = (uint32_t)((16 * sub + keyA) * Geo::kRowBytes + 8 * t);   // K row keyA: block 0 scale; payload bytes + 2
+    const uint32_t t8_va = (uint32_t)(Geo::kVOff + (16 * sub + 4 * t) * Geo::kRowBytes + 4 * g);  // V rows 4t..: payload word + 2
+    const uint32_t t8_sa = (uint32_t)((16 * sub + keyA) * Geo::kRowBytes);           // scales of rows keyA (+ 2 rows: keyB)
+    auto t8_tile = [&](uint32_t sb, int key0, bool staged_mask, uint64_t* empty_bar) {
+        if constexpr (T8) {
+        const int kvA = key0 + 16 * sub + keyA, kvB = kvA + 2;
+        const bool vA_ok = kvA < p.n_kv, vB_ok = kvB < p.n_kv;  // rows past a ragged end hold stale bytes: a zero scale keeps them out
+        // V operands of the tile: aligned words holding payload bytes 0,1 / 2,3 of the lane's word of keys 4t + i, and the block
+        // scales of keys keyA / keyB.  Where they are loaded decides how long the stage is held (B200FA_T8_VLOAD: 0 = per block
+        // inside the P.V loop, 1 = after the scores, before the softmax, 2 = before anything else).
+        uint32_t vlo[NB][4], vhi[NB][4], vsc[NB][2];
+        auto load_v = [&](int b) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t ad = sb + t8_va + i * Geo::kRowBytes + b * kQ8BlockBytes;  // 2 bytes before the payload word
+                if ((b & 1) == 0) { vlo[b][i] = lds32(ad); vhi[b][i] = lds32(ad + 4); }
+                else vlo[b][i] = vhi[b][i] = lds32(ad + 2);
+            }
+            vsc[b][0] = vA_ok ? lds_u16(sb + Geo::kVOff + t8_sa + b * kQ8BlockBytes) : 0u;
+            vsc[b][1] = vB_ok ? lds_u16(sb + Geo::kVOff + t8_sa + 2 * Geo::kRowBytes + b * kQ8BlockBytes) : 0u;
+        };
+        auto release = [&]() {  // every byte of the stage has been read: hand it back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar);
+        };
+#ifndef B200FA_T8_VLOAD
+#define B200FA_T8_VLOAD 0
+#endif
+        if constexpr (B200FA_T8_VLOAD == 2) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) load_v(b);
+        }
+        // ---- S^T = K Q^T ----
+        float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [key slot g / g+8][row 2t / 2t+1]
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            uint32_t h[2][4];  // converted pairs of rows keyA / keyB
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const uint32_t ad = sb + t8_ka + r * 2 * Geo::kRowBytes + b * kQ8BlockBytes;  // 2 bytes before the lane's 8 payload bytes
+                if ((b & 1) == 0) {  // payload at 2 mod 4: bytes 2,3 of w0, all of w1, bytes 0,1 of w2
+                    const uint32_t w0 = lds32(ad) ^ 0x80808080u, w1 = lds32(ad + 4) ^ 0x80808080u, w2 = lds32(ad + 8) ^ 0x80808080u;
+                    h[r][0] = prmt(w0, 0x64646464u, 0x4342); h[r][1] = prmt(w1, 0x64646464u, 0x4140);
+                    h[r][2] = prmt(w1, 0x64646464u, 0x4342); h[r][3] = prmt(w2, 0x64646464u, 0x4140);
+                } else {             // word aligned
+                    const uint32_t w0 = lds32(ad + 2) ^ 0x80808080u, w1 = lds32(ad + 6) ^ 0x80808080u;
+                    h[r][0] = prmt(w0, 0x64646464u, 0x4140); h[r][1] = prmt(w0, 0x64646464u, 0x4342);
+                    h[r][2] = prmt(w1, 0x64646464u, 0x4140); h[r][3] = prmt(w1, 0x64646464u, 0x4342);
+                }
+            }
+            float c[4];
+            mma_16816_c(c, h[0][0], h[1][0], h[0][1], h[1][1], qb[b][0], qb[b][1], qsn[b][0], qsn[b][1], qsn[b][0], qsn[b][1]);
+            mma_16816(c, h[0][2], h[1][2], h[0][3], h[1][3], qb[b][2], qb[b][3]);
+            const float dA = h_bits_to_f(lds_u16(sb + t8_sa + b * kQ8BlockBytes));
+            const float dB = h_bits_to_f(lds_u16(sb + t8_sa + 2 * Geo::kRowBytes + b * kQ8BlockBytes));
+            s[0][0] = fmaf(c[0], dA, s[0][0]); s[0][1] = fmaf(c[1], dA, s[0][1]);
+            s[1][0] = fmaf(c[2], dB, s[1][0]); s[1][1] = fmaf(c[3], dB, s[1][1]);
+        }
+        if constexpr (B200FA_T8_VLOAD == 1) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) load_v(b);
+        }
+        uint32_t mkh[2][2] = {{0u, 0u}, {0u, 0u}};  // mask halves [row][keyA / keyB]
+        if (p.mask != nullptr) {
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                if (staged_mask) {
+                    const uint32_t ma = sb + Geo::kMaskOff + iq1r[rr] * 128 + (16 * sub + keyA) * 2;
+                    mkh[rr][0] = lds_u16(ma); mkh[rr][1] = lds_u16(ma + 4);
+                } else {
+                    mkh[rr][0] = kvA < p.n_kv ? ld_u16(mrow[rr] + (int64_t)kvA * 2) : 0u;
+                    mkh[rr][1] = kvB < p.n_kv ? ld_u16(mrow[rr] + (int64_t)kvB * 2) : 0u;
+                }
+            }
+        }
+        if constexpr (B200FA_T8_VLOAD != 0) release();
+        // ---- scale, mask, lazy online softmax ----
+        float x[2][2];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const float ms = EXT ? mslope[rr] : kLog2e;
+            const float mA = h_bits_to_f(mkh[rr][0]) * ms, mB = h_bits_to_f(mkh[rr][1]) * ms;
+            if (EXT && p.cap_in != 0.f) {
+                x[0][rr] = fmaf(fa_tanh(s[0][rr] * p.cap_in), p.cap_out, mA);
+                x[1][rr] = fmaf(fa_tanh(s[1][rr] * p.cap_in), p.cap_out, mB);
+            } else {
+                x[0][rr] = fmaf(s[0][rr], p.scale_log2, mA);
+                x[1][rr] = fmaf(s[1][rr], p.scale_log2, mB);
+            }
+            if (kvA >= lim[rr]) x[0][rr] = -INFINITY;
+            if (kvB >= lim[rr]) x[1][rr] = -INFINITY;
+        }
+        const float ml0 = fmaxf(x[0][0], x[1][0]), ml1 = fmaxf(x[0][1], x[1][1]);
+        if (__any_sync(0xffffffffu, ml0 > m_run[0] + kLazy || ml1 > m_run[1] + kLazy)) {
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                float mx = rr == 0 ? ml0 : ml1;
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                const float m_new = fmaxf(m_run[rr], mx);
+                const float alpha = fast_exp2(m_run[rr] - ((m_new == -INFINITY) ? 0.f : m_new));  // m_run = -inf -> 0
+                l_run[rr] *= alpha;
+#pragma unroll
+                for (int mt = 0; mt < NMT; mt++) { oT[mt][rr] *= alpha; oT[mt][2 + rr] *= alpha; }
+                m_run[rr] = m_new;
+            }
+        }
+        float pp[2][2];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const float mu = (m_run[rr] == -INFINITY) ? 0.f : m_run[rr];
+            pp[0][rr] = fast_exp2(x[0][rr] - mu);
+            pp[1][rr] = fast_exp2(x[1][rr] - mu);
+            l_run[rr] += pp[0][rr] + pp[1][rr];
+        }
+        // ---- O^T += V^T P'^T ----
+        const uint32_t ph[2] = {pack_half2(pp[0][0], pp[0][1]), pack_half2(pp[1][0], pp[1][1])};  // (rows 2t, 2t+1) of keys keyA, keyB
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            // P' = RN_f16(RN_f16(p) * dV): one packed multiply per key with the scale broadcast to both halves
+            if constexpr (B200FA_T8_VLOAD == 0) {
+                load_v(b);
+                if (b == NB - 1) release();
+            }
+            const __half dA = __ushort_as_half((unsigned short)vsc[b][0]), dB = __ushort_as_half((unsigned short)vsc[b][1]);
+            const __half2 qA = __hmul2(*reinterpret_cast<const __half2*>(&ph[0]), __half2half2(dA));
+            const __half2 qB = __hmul2(*reinterpret_cast<const __half2*>(&ph[1]), __half2half2(dB));
+            const uint32_t bf0 = movmatrix_trans(*reinterpret_cast<const uint32_t*>(&qA));
+            const uint32_t bf1 = movmatrix_trans(*reinterpret_cast<const uint32_t*>(&qB));
+            const uint32_t(&lo)[4] = vlo[b];
+            const uint32_t(&hi)[4] = vhi[b];
+            const uint32_t s0 = (b & 1) == 0 ? 0x6622u : 0x4400u, s1 = (b & 1) == 0 ? 0x7733u : 0x5511u;  // bytes 0,1 of the payload word
+            const uint32_t s2 = (b & 1) == 0 ? 0x4400u : 0x6622u, s3 = (b & 1) == 0 ? 0x5511u : 0x7733u;  // bytes 2,3
+            auto cv = [](uint32_t z) {  // (byte, byte) of two keys -> (q, q) in f16
+                uint32_t y;
+                const uint32_t bias = 0x64806480u;
+                asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(y) : "r"(z), "r"(0x00FF00FFu), "r"(bias));  // (z & 0x00ff00ff) ^ 0x64806480
+                __half2 r = __hsub2(*reinterpret_cast<const __half2*>(&y), *reinterpret_cast<const __half2*>(&bias));
+                return *reinterpret_cast<uint32_t*>(&r);
+            };
+            mma_16816(oT[2 * b], cv(prmt(lo[0], lo[1], s0)), cv(prmt(lo[0], lo[1], s1)), cv(prmt(lo[2], lo[3], s0)), cv(prmt(lo[2], lo[3], s1)), bf0, bf1);
+            mma_16816(oT[2 * b + 1], cv(prmt(hi[0], hi[1], s2)), cv(prmt(hi[0], hi[1], s3)), cv(prmt(hi[2], hi[3], s2)), cv(prmt(hi[2], hi[3], s3)), bf0, bf1);
+        }
+        }
+    };
+    auto t8_slot_st = [&]() {  // [k][lane]: k < KO: oT[k >> 2][k & 3];  KO + 2rr: m of row 2t + rr;  KO + 2rr + 1: its l
+        if constexpr (T8) {
+        float* sp = merge + warp * (Mrg::kSlotBytes / 4) + lane;
+#pragma unroll
+        for (int mt = 0; mt < NMT; mt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) sp[(mt * 4 + e) * 32] = oT[mt][e];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) { sp[(KO + 2 * rr) * 32] = m_run[rr]; sp[(KO + 2 * rr + 1) * 32] = l_run[rr]; }
+        }
+    };
+    DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 0, dk_now());
 
     // ---- fused sequence-parallel step: where the unit triples go, and what the last CTA of the rank does ----
     int units_done = 0;  // units whose final triple this CTA has written
@@ -524,7 +815,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const int64_t n_out = p.total_rows * D;
         const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;  // share ~ units published
         const float* part = reinterpret_cast<const float*>(a.peers[a.rank] + kXchgHeader) + sp_n_floats + sp_gen_off;
-        for (int64_t idx = lo + threadIdx.x; idx < hi; idx += DK_CWARPS * 32) {
+        for (int64_t idx = lo + threadIdx.x; idx < hi; idx += CW * 32) {
             const int64_t row = idx / D;
             const int d = (int)(idx % D);
             float M = -INFINITY;
@@ -552,17 +843,65 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     int n_def = 0, def_u[2] = {0, 0}, def_c0[2] = {0, 0}, def_n[2] = {0, 0};  // partial units of this CTA (at most the first and the last segment)
     int cl_u = 0, cl_n = 1;  // cluster mode: the CTA's single unit and its contributor count
     while (i < my_chunks) {
-        const long long x = start + i;
-        const int u = (int)(x / a.cph), ch0 = (int)(x - (long long)u * a.cph);
+        const unsigned x = start + i;
+        const int u = (int)(x / (unsigned)a.cph), ch0 = (int)(x - (unsigned)u * (unsigned)a.cph);
         const int seg_end = min(my_chunks, i + (a.cph - ch0));
         const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
         // who else works on this unit (off the critical path: the segment's first stage is still in flight)
-        const long long c0 = dk_owner((long long)u * a.cph, a.total, G), c1 = dk_owner((long long)(u + 1) * a.cph - 1, a.total, G);
+        const unsigned c0 = dk_owner((unsigned)u * a.cph, total, G), c1 = dk_owner((unsigned)(u + 1) * a.cph - 1u, total, G);
         const int n_contrib = (int)(c1 - c0 + 1);
 
         // ---- Q fragments of this unit's rows (f16; an f32 Q is rounded like the reference does, flash-llama.h:80) ----
+        if constexpr (T8) {
+            // B fragments: lane (g, t) holds Q[row g][32b + 8t .. + 7]; then -1152 x the block sums of rows 2t, 2t+1
+            const bool qv = g < rows_total;
+            const int qi1 = (qv ? g : 0) / p.gqa, qh = ik2 * p.gqa + (qv ? g : 0) % p.gqa;
+            const char* qrow = p.q + (int64_t)qi1 * p.nb01 + (int64_t)qh * p.nb02 + (int64_t)iq3 * p.nb03;
+            // (all loads first: the shuffles below are ordered against memory operations, and one load -> shuffle chain per block
+            // made the prologue four L2 round trips long)
+            if (!qv) {
 #pragma unroll
-        for (int h = 0; h < RH; h++) {
+                for (int b = 0; b < NB; b++) qb[b][0] = qb[b][1] = qb[b][2] = qb[b][3] = 0u;
+            } else if (p.q_type == B200FA_TYPE_F16) {
+                uint4 v[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++) v[b] = *reinterpret_cast<const uint4*>(qrow + (32 * b + 8 * t) * 2);
+#pragma unroll
+                for (int b = 0; b < NB; b++) { qb[b][0] = v[b].x; qb[b][1] = v[b].y; qb[b][2] = v[b].z; qb[b][3] = v[b].w; }
+            } else {
+                float4 v[NB], y[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    v[b] = *reinterpret_cast<const float4*>(qrow + (32 * b + 8 * t) * 4);
+                    y[b] = *reinterpret_cast<const float4*>(qrow + (32 * b + 8 * t) * 4 + 16);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    qb[b][0] = pack_half2(v[b].x, v[b].y); qb[b][1] = pack_half2(v[b].z, v[b].w);
+                    qb[b][2] = pack_half2(y[b].x, y[b].y); qb[b][3] = pack_half2(y[b].z, y[b].w);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                float ps = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qb[b][w]));
+                    ps += f.x + f.y;
+                }
+                ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+                ps += __shfl_xor_sync(0xffffffffu, ps, 2);   // block sum of row g, in every lane of the quad
+                qsn[b][0] = -1152.f * __shfl_sync(0xffffffffu, ps, (2 * t) * 4);
+                qsn[b][1] = -1152.f * __shfl_sync(0xffffffffu, ps, (2 * t + 1) * 4);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++)
+                if constexpr (EXT) mslope[rr] = kLog2e * fa_slope(p, ik2 * p.gqa + rq[rr]);
+#pragma unroll
+            for (int mt = 0; mt < NMT; mt++) oT[mt][0] = oT[mt][1] = oT[mt][2] = oT[mt][3] = 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < (T8 ? 0 : RH); h++) {
             if constexpr (EXT) mslope[h] = kLog2e * fa_slope(p, ik2 * p.gqa + rq[h]);
             const char* qrow = p.q + (int64_t)iq1r[h] * p.nb01 + (int64_t)(ik2 * p.gqa + rq[h]) * p.nb02 + (int64_t)iq3 * p.nb03;
 #pragma unroll
@@ -582,26 +921,39 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
         }
 #pragma unroll
-        for (int n = 0; n < NT; n++)
+        for (int n = 0; n < (T8 ? 0 : NT); n++)
 #pragma unroll
             for (int e = 0; e < 4; e++) o[n][e] = 0.f;
 #pragma unroll
-        for (int h = 0; h < RH; h++) { m_run[h] = -INFINITY; l_run[h] = 0.f; }
+        for (int h = 0; h < NR; h++) { m_run[h] = -INFINITY; l_run[h] = 0.f; }
 
-        // ---- this warp group's chunks of the segment ----
-        for (int j = i + ((group ^ i) & 1); j < seg_end; j += 2) {
+        // ---- this warp group's chunks of the segment: chunk j belongs to group j % NG ----
+        if (i == 0) asm volatile("bar.sync 3, %0;" ::"n"(dk_threads<T8>()) : "memory");  // the mbarriers are initialised (the producers do not wait here)
+        const int j0 = i + (group + NG - i % NG) % NG;
+        int stage = j0 % NS, phase = (j0 / NS) & 1;  // advanced by NG per chunk: the ring depth is a multiple of NG
+        for (int j = j0; j < seg_end; j += NG, stage += NG) {
+            if (stage >= NS) { stage -= NS; phase ^= 1; }
             const int key0 = (ch0 + (j - i)) * DK_CHUNK;
             const int kv0 = key0 + 16 * sub;
-            const int stage = j % NS;
-            mbar_wait(&full[stage], (j / NS) & 1);
+            DK_TL(threadIdx.x == 0 && j == 0, blockIdx.x * 8 + 6, dk_now());  // ready for the first chunk
+            mbar_wait(&full[stage], phase);
             __syncwarp();
-            if (stamp && j == 0) a.timeline[blockIdx.x * 8 + 1] = dk_now();
-            const bool cstamp = a.timeline != nullptr && blockIdx.x == 0 && sub == 0 && lane == 0 && j < 512;  // per-chunk diagnostics of CTA 0
-            if (cstamp) a.timeline[DK_TL_CHUNK0 + j * 4 + 2] = dk_now();  // chunk landed (as seen by its first consumer warp)
+            DK_TL(threadIdx.x == 0 && j == 0, blockIdx.x * 8 + 1, dk_now());
+            DK_TL(blockIdx.x == 0 && sub == 0 && lane == 0 && j < 512, DK_TL_CHUNK0 + j * 4 + 2, dk_now());  // chunk landed (as seen by its first consumer warp)
+            const bool live = kv0 < a.kv_end && !DK_DBG_SKIP_MATH;
+            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes;
+            if constexpr (T8) {
+                if (live) {
+                    t8_tile(sb, key0, a.mask_bulk && key0 + DK_CHUNK <= p.n_kv, &empty[stage]);  // hands the stage back after its last load
+                } else {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                }
+                DK_TL(blockIdx.x == 0 && sub == 0 && lane == 0 && j < 512, DK_TL_CHUNK0 + j * 4 + 3, dk_now());  // tile done
+                continue;
+            }
             Tile T;
             float s[2][4];
-            const bool live = kv0 < a.kv_end && p.dbg_mode != 1;  // tuning aid (env B200FA_DBG_MODE=1): stream the chunks, touch nothing
-            const uint32_t sb = stages_u32 + stage * Geo::kStageBytes;
             if (live) {
                 read_k(T, sb, kv0, a.mask_bulk && key0 + DK_CHUNK <= p.n_kv);
                 qk_tile(T, s);
@@ -618,51 +970,72 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);  // fragments are in registers: hand the stage back
-            if (cstamp) a.timeline[DK_TL_CHUNK0 + j * 4 + 3] = dk_now();
+            DK_TL(blockIdx.x == 0 && sub == 0 && lane == 0 && j < 512, DK_TL_CHUNK0 + j * 4 + 3, dk_now());  // stage released
             if (live) softmax_pv_tile(T, s, kv0);
         }
 
-        // ---- fold the eight warps' partial states: every warp parks its (m, l, O) in its slot, then thread (lane, warp)
-        //      combines O elements [warp*KPT, +KPT) of that lane across the eight slots and stores them ----
-        if (stamp) a.timeline[blockIdx.x * 8 + 2] = dk_now();
+        // Cluster mode, first barrier: every CTA of the unit has consumed its last chunk, so the leader's ring (where the records go)
+        // is idle.  Arrive now, wait just before the first remote store: the local fold runs in between.
+        if (a.cluster_k > 1) cluster_arrive();
+        // ---- fold the consumer warps' partial states: every warp parks its (m, l, O) in its slot, then thread (lane, warp)
+        //      combines O elements warp, warp + CW, ... of that lane across the slots and stores them ----
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 2, dk_now());
 #pragma unroll
-        for (int h = 0; h < RH; h++) {
-            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
-            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+        for (int h = 0; h < NR; h++) {  // the lane's l covers its own keys: sum over the lanes that share the row
+            if constexpr (T8) {
+                l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 4);
+                l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 8);
+                l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 16);
+            } else {
+                l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+                l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+            }
         }
         bar_consumers();  // everyone is done reading the slots of the previous segment
-        slot_st();
+        if constexpr (T8) t8_slot_st(); else slot_st();
         bar_consumers();
+        if (a.cluster_k > 1) cluster_wait();
         {
-            float wgt[DK_CWARPS][RH], Ms[RH], Ls[RH];
+            float wgt[CW][NR], Ms[NR], Ls[NR];
             const float* sl0 = merge + lane;
 #pragma unroll
-            for (int h = 0; h < RH; h++) {
+            for (int h = 0; h < NR; h++) {
                 float M = -INFINITY;
 #pragma unroll
-                for (int w = 0; w < DK_CWARPS; w++) M = fmaxf(M, sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h) * 32]);
+                for (int w = 0; w < CW; w++) M = fmaxf(M, sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h) * 32]);
                 const float Mu = (M == -INFINITY) ? 0.f : M;
                 float L = 0.f;
 #pragma unroll
-                for (int w = 0; w < DK_CWARPS; w++) {
+                for (int w = 0; w < CW; w++) {
                     wgt[w][h] = fast_exp2(sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h) * 32] - Mu);
                     L += sl0[w * (Mrg::kSlotBytes / 4) + (KO + 2 * h + 1) * 32] * wgt[w][h];
                 }
                 Ms[h] = M; Ls[h] = L;
             }
 #pragma unroll
-            for (int kk = 0; kk < KPT; kk++) {
-                const int k = warp * KPT + kk;
-                const int n = k / (2 * RH), e = k % (2 * RH), h = e >> 1, e1 = e & 1;
+            for (int k = warp; k < KO; k += CW) {
+                // element k of the lane's fragment -> (row R, head dim d); `first`: one thread per row also stores (m, l)
+                int h, R, d;
+                bool first;
+                if constexpr (T8) {
+                    const int mt = k >> 2, e = k & 3, mm = g + 8 * (e >> 1);
+                    h = e & 1; R = 2 * t + h;
+                    d = 32 * (mt >> 1) + 4 * (mm & 7) + 2 * (mt & 1) + (mm >> 3);
+                    first = (mt == 0 && (e >> 1) == 0 && g == 0);
+                } else {
+                    const int n = k / (2 * RH), e = k % (2 * RH), e1 = e & 1;
+                    h = e >> 1; R = g + 8 * h;
+                    d = 64 * (n >> 3) + 16 * t + (n & 7) + 8 * e1;
+                    first = (n == 0 && e1 == 0 && t == 0);
+                }
                 float acc = 0.f;
 #pragma unroll
-                for (int w = 0; w < DK_CWARPS; w++) acc += sl0[w * (Mrg::kSlotBytes / 4) + k * 32] * wgt[w][RH == 1 ? 0 : h];
-                const int R = g + 8 * h;
+                // (h is not a compile-time value: selects, not indexed local arrays)
+                for (int w = 0; w < CW; w++) acc += sl0[w * (Mrg::kSlotBytes / 4) + k * 32] * ((NR == 1 || h == 0) ? wgt[w][0] : wgt[w][NR - 1]);
                 if (R >= rows_total) continue;
-                const int d = 64 * (n >> 3) + 16 * t + (n & 7) + 8 * e1;
-                const int64_t orow = ((int64_t)iq3 * p.n_q + iq1r[RH == 1 ? 0 : h]) * p.n_head + ik2 * p.gqa + rq[RH == 1 ? 0 : h];  // flash-llama.h:434
-                const float M = Ms[RH == 1 ? 0 : h], L = Ls[RH == 1 ? 0 : h];
-                const bool first = (n == 0 && e1 == 0 && t == 0);  // one thread per row also stores (m, l)
+                const int row_q1 = (NR == 1 || h == 0) ? iq1r[0] : iq1r[NR - 1], row_h = (NR == 1 || h == 0) ? rq[0] : rq[NR - 1];
+                const int64_t orow = ((int64_t)iq3 * p.n_q + row_q1) * p.n_head + ik2 * p.gqa + row_h;  // flash-llama.h:434
+                const float M = (NR == 1 || h == 0) ? Ms[0] : Ms[NR - 1], L = (NR == 1 || h == 0) ? Ls[0] : Ls[NR - 1];
                 if (n_contrib > 1 && a.cluster_k > 1) {
                     // record [rank][row][D + 2] in the leader CTA's (drained) stage ring; the cluster barrier below orders these
                     // remote stores before the leader's loads.  The leader's own ring is idle: a cluster CTA has one segment,
@@ -691,7 +1064,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
         }
         if (n_contrib == 1) units_done++;
-        if (stamp) a.timeline[blockIdx.x * 8 + 3] = dk_now();
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 3, dk_now());
         // Units shared with other CTAs are signalled and merged after the CTA's whole run (below): only its first and its
         // last segment can be partial units, and a fence + atomic round trip in the middle of the stream would stall the
         // consumers for longer than the ring can cover.
@@ -710,7 +1083,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const int u = cl_u, n_contrib = cl_n;
         const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
         const float* recs = reinterpret_cast<const float*>(smem);
-        for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
+        for (int idx = threadIdx.x; idx < rows_total * D; idx += CW * 32) {
             const int R = idx / D, d = idx % D;
             float M = -INFINITY;
             for (int cc = 0; cc < n_contrib; cc++) M = fmaxf(M, recs[(cc * RLIVE + R) * (D + 2) + D]);
@@ -738,7 +1111,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
         }
         units_done++;
-        if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; }
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now()); DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, slot_idx);
         finish_seqpar();
         return;
     }
@@ -747,7 +1120,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     //      (fa_reduce, flash_row_float.h:415-472: M = max m_i, L = sum l_i 2^(m_i-M), O = sum O~_i 2^(m_i-M) / L —
     //      here one parallel fp32 pass) ----
     if (n_def == 0) {
-        if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; }
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now()); DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, slot_idx);
         finish_seqpar();
         return;
     }
@@ -763,13 +1136,13 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const int u = def_u[k], n_contrib = def_n[k];
         const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
         bar_consumers();  // s_tab is reused
-        for (int cc = threadIdx.x; cc < n_contrib; cc += DK_CWARPS * 32) {  // record slot of contributor c0 + cc
-            const long long st = (long long)(def_c0[k] + cc) * a.total / G;
-            s_tab[cc] = (def_c0[k] + cc) * a.max_slots + (u - (int)(st / a.cph));
+        for (int cc = threadIdx.x; cc < n_contrib; cc += CW * 32) {  // record slot of contributor c0 + cc
+            const unsigned st = (unsigned)(def_c0[k] + cc) * total / G;
+            s_tab[cc] = (def_c0[k] + cc) * a.max_slots + (u - (int)(st / (unsigned)a.cph));
         }
         bar_consumers();
         __threadfence();
-        for (int idx = threadIdx.x; idx < rows_total * D; idx += DK_CWARPS * 32) {
+        for (int idx = threadIdx.x; idx < rows_total * D; idx += CW * 32) {
             const int R = idx / D, d = idx % D;
             // one pass, loads batched MB records at a time (they are independent: ONE L2 round trip for up to 24 contributors — with
             // batches of 8 the merge of an 18-CTA unit took three round trips, ~7 us = a third of the per-GPU C5 step at 8 GPUs)
@@ -816,7 +1189,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         units_done++;
     }
     finish_seqpar();
-    if (stamp) { a.timeline[blockIdx.x * 8 + 4] = dk_now(); a.timeline[blockIdx.x * 8 + 5] = slot_idx; unsigned sm_id; asm("mov.u32 %0, %%smid;" : "=r"(sm_id)); a.timeline[blockIdx.x * 8 + 6] = sm_id; }
+    DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now()); DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, slot_idx);
 }
 
 }  // namespace b200fa
