@@ -171,13 +171,15 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
         if (pl.n_units <= sm_count) {
             const int aligned = pl.n_units * (sm_count / pl.n_units);
             if (aligned * 5 >= sm_count * 4) grid = aligned;
+            // (Tried: 16 CTAs per unit for 8-9 units, so that a unit is one non-portable 16-CTA cluster: on this B200 fewer than eight
+            // such clusters can be resident — cudaOccupancyMaxActiveClusters — and 128 CTAs stream q8_0 slower than 144.)
         }
         if (const char* e = getenv("B200FA_STREAM_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
         // unit-aligned grid with 2..8 CTAs per unit: launch each unit's CTAs as one thread-block cluster (DSMEM merge)
         static const bool no_cluster = getenv("B200FA_NO_CLUSTER") != nullptr;
         if (!no_cluster && pl.n_units > 0 && grid % pl.n_units == 0 && pl.total_chunks >= grid) {
             const int k = grid / pl.n_units;
-            if (k >= 2 && k <= 8) pl.cluster_k = k;
+            if (k >= 2 && k <= 16) pl.cluster_k = k;  // 9..16: non-portable cluster sizes (launch_stream_t checks that they can be resident)
         }
         if (grid > DK_TAB) grid = DK_TAB;
         pl.grid = (int)(pl.total_chunks < grid ? pl.total_chunks : grid);
@@ -324,13 +326,35 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
     // griddepcontrol.wait, before its first global access).  Off for the peer-memory variants and with B200FA_NO_PDL.
     static const bool no_pdl = getenv("B200FA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && a.peers == nullptr;
+    DkArgs args = a;
+    if (args.cluster_k > 8) {
+        // non-portable cluster size: opt in, and use it only if all clusters of the grid can be resident at once (one 16-CTA cluster per
+        // GPC on B200); otherwise the same grid runs without clusters and merges through global records
+        static thread_local int max_clusters[64][17] = {};
+        int& mc = max_clusters[dev >= 0 && dev < 64 ? dev : 0][args.cluster_k];
+        if (mc == 0) {
+            mc = -1;
+            if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT, T8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t qc{};
+                qc.gridDim = dim3(args.cluster_k); qc.blockDim = dim3(dk_threads<T8>()); qc.dynamicSmemBytes = smem;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = args.cluster_k; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                qc.attrs = qa; qc.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, fa_decode_stream<D, KV, RH, EXT, T8>, &qc) == cudaSuccess && n > 0) mc = n;
+            }
+            (void)cudaGetLastError();
+        }
+        if (mc < grid / args.cluster_k) args.cluster_k = 0;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(dk_threads<T8>()); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (a.cluster_k > 1) {
+    if (args.cluster_k > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = a.cluster_k; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        attr[na].val.clusterDim.x = args.cluster_k; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
         na++;
     }
     if (pdl) {
@@ -339,7 +363,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         na++;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT, T8>, p, a, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT, T8>, p, args, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {

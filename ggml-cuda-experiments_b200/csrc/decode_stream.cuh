@@ -340,6 +340,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         }
         __syncwarp();
         if (a.cluster_k > 1) { cluster_sync_all(); cluster_sync_all(); }  // every thread of the cluster takes part in both cluster barriers
+        DK_TL(threadIdx.x == CW * 32, blockIdx.x * 8 + 6, dk_now());  // producer warp 0 leaves
         return;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -935,7 +936,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             if (stage >= NS) { stage -= NS; phase ^= 1; }
             const int key0 = (ch0 + (j - i)) * DK_CHUNK;
             const int kv0 = key0 + 16 * sub;
-            DK_TL(threadIdx.x == 0 && j == 0, blockIdx.x * 8 + 6, dk_now());  // ready for the first chunk
+
             mbar_wait(&full[stage], phase);
             __syncwarp();
             DK_TL(threadIdx.x == 0 && j == 0, blockIdx.x * 8 + 1, dk_now());
@@ -1079,7 +1080,13 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     if (a.cluster_k > 1) {
         // ---- cluster mode: the unit's CTAs are one thread-block cluster; their records sit in the leader's shared memory ----
         cluster_sync_all();
-        if (blockIdx.x % a.cluster_k != 0 || cl_n <= 1) { finish_seqpar(); return; }
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, dk_now());  // past the cluster barrier
+        if (blockIdx.x % a.cluster_k != 0 || cl_n <= 1) {
+            DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now());
+            DK_TL(threadIdx.x == (CW - 1) * 32, blockIdx.x * 8 + 1, dk_now());  // (diagnostic) the last consumer warp leaves
+            finish_seqpar();
+            return;
+        }
         const int u = cl_u, n_contrib = cl_n;
         const int ik2 = u % p.n_head_kv, iq3 = u / p.n_head_kv;
         const float* recs = reinterpret_cast<const float*>(smem);
@@ -1111,7 +1118,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             }
         }
         units_done++;
-        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now()); DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, slot_idx);
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now());
         finish_seqpar();
         return;
     }
@@ -1120,7 +1127,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     //      (fa_reduce, flash_row_float.h:415-472: M = max m_i, L = sum l_i 2^(m_i-M), O = sum O~_i 2^(m_i-M) / L —
     //      here one parallel fp32 pass) ----
     if (n_def == 0) {
-        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now()); DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, slot_idx);
+        DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now());
         finish_seqpar();
         return;
     }
@@ -1131,6 +1138,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         s_flag[threadIdx.x] = (old == (unsigned int)def_n[threadIdx.x] - 1);
     }
     bar_consumers();
+    DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, dk_now());  // records published, arrival counted
     for (int k = 0; k < n_def; k++) {
         if (s_flag[k] == 0) continue;
         const int u = def_u[k], n_contrib = def_n[k];
@@ -1142,54 +1150,100 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         }
         bar_consumers();
         __threadfence();
-        for (int idx = threadIdx.x; idx < rows_total * D; idx += CW * 32) {
-            const int R = idx / D, d = idx % D;
-            // one pass, loads batched MB records at a time (they are independent: ONE L2 round trip for up to 24 contributors — with
-            // batches of 8 the merge of an 18-CTA unit took three round trips, ~7 us = a third of the per-GPU C5 step at 8 GPUs)
-            constexpr int MB = 24;
-            float M = -INFINITY, L = 0.f, acc = 0.f;
-            for (int cb = 0; cb < n_contrib; cb += MB) {
-                float mm[MB], ll[MB], aa[MB];
+        // The merge is a chain of L2 round trips (~0.6 us each under load) on the critical path of the whole launch: it is laid out so
+        // that there are two of them.  (A one-pass version with 72 batched loads per thread spilled in the 128-register transposed
+        // q8_0 kernel, and a version that walked the records eight at a time took ~5 us for an 18-CTA unit.)
+        // Pass 1, one warp per row: the records' (m, l) pairs -> weights 2^(m_c - M) in shared memory (the merge slots are idle), M, L.
+        constexpr int T = CW * 32, D4 = D / 4;
+        float* sw = merge;                                   // [rows_total][n_contrib]
+        float* sML = sw + rows_total * n_contrib;            // [rows_total][2]
+        float4* spart = reinterpret_cast<float4*>(merge + ((rows_total * (n_contrib + 2) + 3) & ~3));  // [groups][rows_total * D/4]
+        for (int R = warp; R < rows_total; R += CW) {
+            float2 ml[(DK_TAB + 31) / 32];
 #pragma unroll
-                for (int e = 0; e < MB; e++) {
-                    const float* rec = a.rec + ((int64_t)s_tab[min(cb + e, n_contrib - 1)] * DK_REC_ROWS + R) * (D + DK_REC_PAD);
-                    mm[e] = __ldcg(rec + D); ll[e] = __ldcg(rec + D + 1); aa[e] = __ldcg(rec + d);
-                }
-                float Mb = M;
-#pragma unroll
-                for (int e = 0; e < MB; e++) if (cb + e < n_contrib) Mb = fmaxf(Mb, mm[e]);
-                const float Mu = (Mb == -INFINITY) ? 0.f : Mb;
-                const float w0 = fast_exp2(M - Mu);  // M = -inf -> 0
-                L *= w0; acc *= w0;
-#pragma unroll
-                for (int e = 0; e < MB; e++) {
-                    if (cb + e < n_contrib) {
-                        const float wt = fast_exp2(mm[e] - Mu);
-                        L += ll[e] * wt; acc += aa[e] * wt;
-                    }
-                }
-                M = Mb;
+            for (int e = 0; e < (DK_TAB + 31) / 32; e++) {
+                const int c = lane + 32 * e;
+                ml[e] = c < n_contrib ? __ldcg(reinterpret_cast<const float2*>(a.rec + ((int64_t)s_tab[c] * DK_REC_ROWS + R) * (D + DK_REC_PAD) + D))
+                                      : make_float2(-INFINITY, 0.f);
             }
+            float M = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < (DK_TAB + 31) / 32; e++) M = fmaxf(M, ml[e].x);
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, sft));
+            const float Mu = (M == -INFINITY) ? 0.f : M;
+            float L = 0.f;
+#pragma unroll
+            for (int e = 0; e < (DK_TAB + 31) / 32; e++) {
+                const int c = lane + 32 * e;
+                const float wt = fast_exp2(ml[e].x - Mu);
+                if (c < n_contrib) sw[R * n_contrib + c] = wt;
+                L += ml[e].y * wt;
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) L += __shfl_xor_sync(0xffffffffu, L, sft);
+            if (lane == 0) { sML[2 * R] = M; sML[2 * R + 1] = L; }
+        }
+        bar_consumers();
+        // Pass 2: the threads form `groups` teams of E4 (one thread per four output elements); team g sums the records c = g, g + groups,
+        // ... with eight 16-byte loads in flight, and the teams' partial sums meet in shared memory.
+        const int E4 = rows_total * D4;
+        const int groups = E4 <= T ? T / E4 : 1;
+        for (int e4 = (int)threadIdx.x % E4, grp = (int)threadIdx.x / E4; grp < groups && e4 < E4; e4 += (groups > 1 ? E4 : T)) {
+            const int R = e4 / D4, d4 = e4 % D4;
+            const float* wr = sw + R * n_contrib;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = grp; c < n_contrib; c += 8 * groups) {
+                float4 v[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int cc = min(c + e * groups, n_contrib - 1);
+                    v[e] = __ldcg(reinterpret_cast<const float4*>(a.rec + ((int64_t)s_tab[cc] * DK_REC_ROWS + R) * (D + DK_REC_PAD)) + d4);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int cc = c + e * groups;
+                    const float wt = cc < n_contrib ? wr[cc] : 0.f;
+                    acc.x = fmaf(v[e].x, wt, acc.x); acc.y = fmaf(v[e].y, wt, acc.y); acc.z = fmaf(v[e].z, wt, acc.z); acc.w = fmaf(v[e].w, wt, acc.w);
+                }
+            }
+            spart[grp * E4 + e4] = acc;
+        }
+        bar_consumers();
+        for (int e4 = threadIdx.x; e4 < E4; e4 += T) {
+            const int R = e4 / D4, d0 = 4 * (e4 % D4);
+            float4 s4 = spart[e4];
+            for (int g2 = 1; g2 < groups; g2++) {
+                const float4 t4 = spart[g2 * E4 + e4];
+                s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
+            }
+            const float M = sML[2 * R], L = sML[2 * R + 1];
+            const float accs[4] = {s4.x, s4.y, s4.z, s4.w};
             const int iq1 = R / p.gqa;
             const int64_t orow = ((int64_t)iq3 * p.n_q + iq1) * p.n_head + ik2 * p.gqa + R % p.gqa;
-            if (p.dst != nullptr) {
-                const float y = L > 0.f ? acc / L : 0.f;
-                if (d < p.Dr) {
-                    if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
-                    else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int d = d0 + e;
+                const float acc = accs[e];
+                if (p.dst != nullptr) {
+                    const float y = L > 0.f ? acc / L : 0.f;
+                    if (d < p.Dr) {
+                        if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
+                        else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
+                    }
+                } else if (a.peers != nullptr) {
+                    emit_triple(orow, d, acc, d == 0, M * kLn2, L);
+                } else {
+                    float* out = p.part_out + orow * (D + 2);
+                    out[d] = acc;
+                    if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
                 }
-            } else if (a.peers != nullptr) {
-                emit_triple(orow, d, acc, d == 0, M * kLn2, L);
-            } else {
-                float* out = p.part_out + orow * (D + 2);
-                out[d] = acc;
-                if (d == 0) { out[D] = M * kLn2; out[D + 1] = L; }
             }
         }
         units_done++;
     }
     finish_seqpar();
-    DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now()); DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 5, slot_idx);
+    DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 4, dk_now());
 }
 
 }  // namespace b200fa

@@ -59,14 +59,14 @@ for it in range(3):
         print(f"  {n:12s} min {col.min():7d}  med {int(np.median(col)):7d}  max {col.max():7d} ns")
     if it == 2:
         order = np.argsort(s[:, 2])
-        print("  per CTA (sorted by end of streaming): cta smid segs | first  stream_end  fold_done  end")
+        print("  per CTA (sorted by end of streaming): cta | first  stream_end  fold_done  end")
         for o in list(order[:6]) + list(order[-24:]):
             r = s[o]
-            print(f"    {o:4d} {r[6]:4d} {r[5]:2d} | {r[1]-t0:6d} {r[2]-t0:6d} {r[3]-t0:6d} {r[4]-t0:6d}")
-        for ns in (1, 2, 3):
-            sel = s[s[:, 5] == ns]
-            if len(sel):
-                print(f"  CTAs with {ns} segment(s): {len(sel)}; stream_end median {int(np.median(sel[:, 2] - t0))}, end median {int(np.median(sel[:, 4] - t0))}")
+            print(f"    {o:4d} | {r[1]-t0:6d} {r[2]-t0:6d} {r[3]-t0:6d} {r[4]-t0:6d}")
+        print("  the 10 CTAs that end last: cta | stream_end fold_done synced end")
+        for o in np.argsort(s[:, 4])[-10:]:
+            r = s[o]
+            print(f"    {o:4d} | {r[2]-t0:6d} {r[3]-t0:6d} {r[5]-t0:6d} {r[4]-t0:6d}   producer exit {r[6]-t0:6d}  idx1 {r[1]-t0:6d}")
 
 # per-chunk view of CTA 0 (ns): stage freed -> operations issued -> landed -> released by the first consumer warp
 ch = ch[(ch[:, 2] > 0)]
