@@ -10,7 +10,7 @@ from .api import (  # noqa: F401
     FLAG_CAUSAL, FLAG_NO_TCGEN05, FLAG_WORKSPACE_ZEROED, TYPE_F16, TYPE_F32, TYPE_Q8_0, B200FAError, ExtParams, PlanInfo, PLAN_PREFILL, PLAN_ROWS16, PLAN_STREAM, plan, Workspace, dequantize_q8_0,
     flash_attn_ext, flash_attn_ext_raw, flash_attn_partial, flash_attn_partial_scatter, flash_attn_seqpar, kv_cache_append, merge_partials_wait, PeerExchange, last_dispatch, last_launch_count, lib, merge_partials,
     quantize_q8_0, workspace_size)
-from .build import build  # noqa: F401
+from .build import build, build_example  # noqa: F401
 from .tensor_io import capture_paths, read_tensor, replay_capture, tensor_info, write_tensor  # noqa: F401
 from .sharding import (  # noqa: F401
     HeadShard, SeqShard, flash_attn_ext_head_parallel, flash_attn_ext_seq_parallel, head_shard, seq_shard, slice_heads)

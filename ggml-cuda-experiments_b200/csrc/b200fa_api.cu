@@ -10,7 +10,6 @@
 #include "decode_stream.cuh"
 #include "prefill_tcgen05.cuh"
 #include "prefill_persistent.cuh"
-#include "prefill_persistent2.cuh"
 #include "q8_0.cuh"
 #include "tensor_file.cuh"
 
@@ -20,7 +19,11 @@ namespace {
 
 thread_local const char* g_last_dispatch = "none";
 thread_local int g_last_launches = 0;
-unsigned long long* g_timeline = nullptr;  // diagnostics: see b200fa_debug_timeline
+#ifdef B200FA_TUNING
+thread_local unsigned long long* g_timeline = nullptr;  // diagnostics: see b200fa_debug_timeline (tuning builds only, per thread)
+#else
+constexpr unsigned long long* g_timeline = nullptr;
+#endif
 
 struct SeqPar { char* const* peers = nullptr; int rank = 0, world = 1; void* fdst = nullptr; int fdst_type = 0; };
 thread_local SeqPar g_seqpar;  // set by b200fa_flash_attn_seqpar around its attn_common call
@@ -89,7 +92,7 @@ bool stream_eligible(const Shape& sh, bool sizing) {
     if (sh.n_head_kv * sh.n_batch > 65536) return false;
     // the kernel's chunk bookkeeping is 32-bit (DK_MAX_TOTAL_X_GRID): out of reach for any K/V a 180 GB device holds, D = 64 q8_0 aside
     if (sh.n_head_kv * sh.n_batch * ((sh.n_kv + DK_CHUNK - 1) / DK_CHUNK) * (DK_TAB + 1) > DK_MAX_TOTAL_X_GRID) return false;
-    static const bool off = getenv("B200FA_DECODE_IMPL") && !strcmp(getenv("B200FA_DECODE_IMPL"), "rows16");
+    static const bool off = tune_env("B200FA_DECODE_IMPL") && !strcmp(tune_env("B200FA_DECODE_IMPL"), "rows16");
     if (off) return false;
     if (sizing || sh.kv_type == B200FA_TYPE_F16) return true;
     // q8_0: the producer copies whole chunks of rows with 16-byte bulk copies -> rows must be contiguous and 16-byte aligned per head
@@ -100,7 +103,7 @@ bool stream_eligible(const Shape& sh, bool sizing) {
 
 // How many virtual KV heads a real one is split into so that a 17..128-row GQA burst fits the stream kernel's 16 rows (1 = no split)
 int virtual_head_split(int64_t n_q, int64_t n_head, int64_t n_head_kv, int64_t n_batch) {
-    static const bool no_vh = getenv("B200FA_NO_VIRTUAL_HEADS") != nullptr;
+    static const bool no_vh = tune_env("B200FA_NO_VIRTUAL_HEADS") != nullptr;
     const int64_t gqa = n_head / n_head_kv, rows = n_q * gqa;
     if (no_vh || rows <= 16 || rows > 128 || n_q > 16 || n_head_kv * n_batch * 8 > 65536) return 1;
     for (int dv = 2; dv <= gqa; dv++)
@@ -117,7 +120,7 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     // P.V too), then the tensor-core kernel — the 16-row fallback re-reads K/V per row group and measured 20 TFLOP/s on C3's shape.
     const int64_t nbk = sh.n_batch_kv > 0 ? sh.n_batch_kv : n_batch;
     const size_t kv16 = sh.kv_type == B200FA_TYPE_Q8_0 ? align_up((size_t)(n_kv * n_head_kv * nbk * D * 2), 256) : 0;
-    static const bool no_q8_prefill = getenv("B200FA_NO_Q8_PREFILL") != nullptr;
+    static const bool no_q8_prefill = tune_env("B200FA_NO_Q8_PREFILL") != nullptr;
     const bool kv_ok = sh.kv_type == B200FA_TYPE_F16 || (!no_q8_prefill && (D == 64 || D == 128) && kv16 <= ((size_t)512 << 20));
     // More than 16 query positions: the tensor-core kernel, even when a 128-row tile is mostly padding (n_q = 32 against 8 K keys:
     // 122 us on the 16-row-group fallback, which re-reads K/V per group, vs ~40 us here with the KV range split over the SMs).
@@ -133,7 +136,7 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
         // Pick the segment count with the shortest makespan (waves / segments) among 2..16 with >= 8 KV tiles per segment and at
         // most 128 MB of partial rows.
         const int64_t n_items = ((qt + 1) / 2) * n_head * n_batch;
-        static const bool no_split = getenv("B200FA_PREFILL_NO_SPLIT") != nullptr;
+        static const bool no_split = tune_env("B200FA_PREFILL_NO_SPLIT") != nullptr;
         if (!no_split && n_items < sm_count && kt >= 16 && kt <= PP_MAX_KV_TILES && (sh.Dr == 0 || sh.Dr == 128)) {
             const size_t row_bytes = (size_t)(n_q * n_head * n_batch) * (128 + 4) * 4;
             int best = 1;
@@ -174,9 +177,9 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
             // (Tried: 16 CTAs per unit for 8-9 units, so that a unit is one non-portable 16-CTA cluster: on this B200 fewer than eight
             // such clusters can be resident — cudaOccupancyMaxActiveClusters — and 128 CTAs stream q8_0 slower than 144.)
         }
-        if (const char* e = getenv("B200FA_STREAM_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
+        if (const char* e = tune_env("B200FA_STREAM_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
         // unit-aligned grid with 2..8 CTAs per unit: launch each unit's CTAs as one thread-block cluster (DSMEM merge)
-        static const bool no_cluster = getenv("B200FA_NO_CLUSTER") != nullptr;
+        static const bool no_cluster = tune_env("B200FA_NO_CLUSTER") != nullptr;
         if (!no_cluster && pl.n_units > 0 && grid % pl.n_units == 0 && pl.total_chunks >= grid) {
             const int k = grid / pl.n_units;
             if (k >= 2 && k <= 16) pl.cluster_k = k;  // 9..16: non-portable cluster sizes (launch_stream_t checks that they can be resident)
@@ -220,7 +223,7 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
             if (eff >= best - 0.03) { want = n; break; }
         }
     }
-    if (const char* e = getenv("B200FA_SPLITS")) want = atoll(e) > 0 ? atoll(e) : want;
+    if (const char* e = tune_env("B200FA_SPLITS")) want = atoll(e) > 0 ? atoll(e) : want;
     int64_t len = (n_kv + want - 1) / want;
     len = (len + 15) / 16 * 16;
     if (len < 16) len = 16;
@@ -284,12 +287,16 @@ int launch_rows16(const FaParams& p, int n_groups, cudaStream_t st) {
         if (e != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev][ti] = true;
     }
-    static const int pipe = getenv("B200FA_DECODE_PIPE") ? atoi(getenv("B200FA_DECODE_PIPE")) : 1;
-    if (ti == 0 && pipe == 0) {
+#ifdef B200FA_TUNING
+    static const int pipe = tune_env("B200FA_DECODE_PIPE") ? atoi(tune_env("B200FA_DECODE_PIPE")) : 1;
+    if (ti == 0 && pipe == 0) {  // the register-double-buffered variant without the cp.async FIFO (measured slower; comparison only)
         static thread_local bool a2[64] = {};
         if (!a2[dev]) { cudaFuncSetAttribute(fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a2[dev] = true; }
         fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, false, EXT><<<grid, block, smem, st>>>(p);
-    } else if (ti == 0) fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, true, EXT><<<grid, block, smem, st>>>(p);
+        return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    }
+#endif
+    if (ti == 0) fa_rows16_splitkv<D, B200FA_TYPE_F16, RH, true, EXT><<<grid, block, smem, st>>>(p);
     else fa_rows16_splitkv<D, B200FA_TYPE_Q8_0, RH, true, EXT><<<grid, block, smem, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
@@ -324,7 +331,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
     }
     // Programmatic dependent launch: this kernel may be scheduled while the previous kernel of the stream drains (it waits in-kernel,
     // griddepcontrol.wait, before its first global access).  Off for the peer-memory variants and with B200FA_NO_PDL.
-    static const bool no_pdl = getenv("B200FA_NO_PDL") != nullptr;
+    static const bool no_pdl = tune_env("B200FA_NO_PDL") != nullptr;
     const bool pdl = !no_pdl && a.peers == nullptr;
     DkArgs args = a;
     if (args.cluster_k > 8) {
@@ -375,11 +382,11 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     a.cluster_k = pl.cluster_k;
     // every CTA's run lies inside one unit (unit-aligned grid, or one chunk per CTA): the fold follows the CTA's last chunk, the deep ring applies
     a.deep_ring = (pl.grid > 0 && pl.n_units > 0 && pl.grid % pl.n_units == 0 && pl.total_chunks >= pl.grid) ? 1 : 0;
-    { static const bool nd = getenv("B200FA_NO_DEEP_RING") != nullptr; if (nd) a.deep_ring = 0; }
-    { static const int rg = getenv("B200FA_RING") ? atoi(getenv("B200FA_RING")) : 0; a.ring = rg; }
+    { static const bool nd = tune_env("B200FA_NO_DEEP_RING") != nullptr; if (nd) a.deep_ring = 0; }
+    { static const int rg = tune_env("B200FA_RING") ? atoi(tune_env("B200FA_RING")) : 0; a.ring = rg; }
     a.peers = g_seqpar.peers; a.rank = g_seqpar.rank; a.world = g_seqpar.world; a.fdst = g_seqpar.fdst; a.fdst_type = g_seqpar.fdst_type;
     a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
-    { static const bool nb = getenv("B200FA_NO_MASK_BULK") != nullptr; if (nb) a.mask_bulk = 0; }
+    { static const bool nb = tune_env("B200FA_NO_MASK_BULK") != nullptr; if (nb) a.mask_bulk = 0; }
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {
         if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv / p.kv_div, p.n_batch_kv, p.nb11, p.nb12, p.nb13, DK_CHUNK, p.Dr)) return B200FA_ERR_CUDA;
@@ -388,7 +395,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     const bool q8 = p.kv_type == B200FA_TYPE_Q8_0;
     if (q8) {
         // the contiguous rows of a head as a [lines][128 B] byte tensor (whole lines only: nothing past the head is ever read)
-        static const bool no_lines = getenv("B200FA_Q8_BULK1D") != nullptr;
+        static const bool no_lines = tune_env("B200FA_Q8_BULK1D") != nullptr;
         const int64_t lines = (int64_t)p.n_kv * (p.D / kQ8BlockElems * kQ8BlockBytes) / 128;
         if (!no_lines && lines > 0) {
             const int box_lines = DK_CHUNK * (p.D / kQ8BlockElems * kQ8BlockBytes) / 128;
@@ -397,7 +404,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
             a.q8_lines = (int)(lines > 0x7fffffff ? 0x7fffffff : lines);
         }
     }
-    static const int force_rh = getenv("B200FA_STREAM_RH") ? atoi(getenv("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
+    static const int force_rh = tune_env("B200FA_STREAM_RH") ? atoi(tune_env("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
     const bool small = (int64_t)p.n_q * p.gqa <= 8 && force_rh != 2;
     g_last_launches++;
     const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
@@ -405,7 +412,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
 #define B200FA_STREAM(DD, KK) (ext ? B200FA_STREAM_E(DD, KK, true) : B200FA_STREAM_E(DD, KK, false))
 #define B200FA_STREAM_T8(DD) (ext ? launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, true, true>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, false, true>(p, a, pl.grid, tk, tv, st))
     // q8_0 units of at most 8 rows: the transposed tile (decode_stream.cuh, T8)
-    static const bool q8_rowmajor = getenv("B200FA_Q8_ROWMAJOR") != nullptr;
+    static const bool q8_rowmajor = tune_env("B200FA_Q8_ROWMAJOR") != nullptr;
     if (q8 && small && !q8_rowmajor) return p.D == 128 ? B200FA_STREAM_T8(128) : B200FA_STREAM_T8(64);
     if (p.D == 128) return q8 ? B200FA_STREAM(128, B200FA_TYPE_Q8_0) : B200FA_STREAM(128, B200FA_TYPE_F16);
     return q8 ? B200FA_STREAM(64, B200FA_TYPE_Q8_0) : B200FA_STREAM(64, B200FA_TYPE_F16);
@@ -437,12 +444,22 @@ int b200fa_tensor_file_write(const char* path, const char* name, int type, int n
     return tf_write(path, name, type, n_dims, ne, data);
 }
 void b200fa_debug_set(void* timeout_word, float* dump, int dump_cta) {
+#ifdef B200FA_TUNING
     pf_debug().dbg = (unsigned long long*)timeout_word;
     pf_debug().dump = dump;
     pf_debug().dump_cta = dump_cta;
+#else
+    (void)timeout_word; (void)dump; (void)dump_cta;  // inert in the shipped library
+#endif
 }
 const char* b200fa_last_dispatch(void) { return g_last_dispatch; }
-void b200fa_debug_timeline(void* stamps) { g_timeline = (unsigned long long*)stamps; }
+void b200fa_debug_timeline(void* stamps) {
+#ifdef B200FA_TUNING
+    g_timeline = (unsigned long long*)stamps;
+#else
+    (void)stamps;  // inert in the shipped library
+#endif
+}
 int b200fa_last_launch_count(void) { return g_last_launches; }
 
 size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
@@ -525,7 +542,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.kv_pos0 = kv_pos0;
     p.causal_off = n_kv_total - ne01;
     p.total_rows = ne03 * ne01 * ne02;
-    { static const int dm = getenv("B200FA_DBG_MODE") ? atoi(getenv("B200FA_DBG_MODE")) : 0; p.dbg_mode = dm; }
+    { static const int dm = tune_env("B200FA_DBG_MODE") ? atoi(tune_env("B200FA_DBG_MODE")) : 0; p.dbg_mode = dm; }
     if (max_bias > 0.f) {  // ALiBi slopes (upstream ggml: m0 = 2^(-max_bias/n_head_log2), m1 = 2^(-(max_bias/2)/n_head_log2))
         int nhl2 = 1;
         while (nhl2 * 2 <= (int)ne02) nhl2 *= 2;
@@ -556,7 +573,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
             p.kv_type = B200FA_TYPE_F16;
             p.nb11 = p.nb21 = ne00 * 2; p.nb12 = p.nb22 = ne11 * ne00 * 2; p.nb13 = p.nb23 = ne12 * ne11 * ne00 * 2;
         }
-        static const bool per_cta = getenv("B200FA_PREFILL") && !strcmp(getenv("B200FA_PREFILL"), "cta");
+        static const bool per_cta = tune_env("B200FA_PREFILL") && !strcmp(tune_env("B200FA_PREFILL"), "cta");
         if ((per_cta && p.Dr == PF_D) || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
             rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
         } else {

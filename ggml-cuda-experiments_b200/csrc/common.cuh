@@ -6,7 +6,18 @@
 
 #include "../../include/b200fa.h"
 
+#include <stdlib.h>
+
 namespace b200fa {
+
+// Tuning knobs are environment variables that exist ONLY in -DB200FA_TUNING builds (ggml-cuda-experiments_b200/build.py
+// build(tuning=True) -> libb200fa_tuning.so, used by the profiles/ tools).  In the shipped library tune_env() is the constant
+// nullptr: no getenv, no process-global switches, and the variants they select are folded away.
+#ifdef B200FA_TUNING
+inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+inline const char* tune_env(const char*) { return nullptr; }
+#endif
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

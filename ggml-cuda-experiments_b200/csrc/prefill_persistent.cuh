@@ -543,4 +543,106 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     }
 }
 
+// n_seg > 1: split-KV prefill — `part` ([n_seg][total_rows][D + 4] f32, in the workspace) receives the segments' partial rows and
+// fa_combine_pad merges them into dst in a second launch.
+inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_bytes, unsigned int* counters, int sm_count,
+                                     cudaStream_t st, int* launches, int n_seg = 1, float* part = nullptr) {
+    if (p.D != PF_D || p.kv_type != B200FA_TYPE_F16 || !(p.scale > 0.f) || p.n_kv > PP_MAX_KV_TILES * PF_BN) return B200FA_ERR_UNSUPPORTED;
+    // Head sizes below 128 (Dr, a multiple of 8) run on the same 128-wide kernel: the tensor maps describe rows of Dr elements,
+    // so TMA zero-fills columns Dr..127 of every Q/K/V tile on the way in (zeros add nothing to Q.K^T, and the P.V columns they
+    // produce are never stored: the dst tensor map clips them on the way out).
+    const int Dr = p.Dr;
+    int n = 0;
+    const void* qbase = p.q;
+    int64_t qnb1 = p.nb01, qnb2 = p.nb02, qnb3 = p.nb03;
+    if (p.q_type == B200FA_TYPE_F32) {
+        __half* q16 = reinterpret_cast<__half*>(ws);
+        const int64_t work = p.total_rows * (Dr / 8);
+        fa_q_to_f16<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p.q, q16, Dr, p.n_q, p.n_head, p.total_rows, p.nb01, p.nb02,
+                                                                   p.nb03);
+        n++;
+        qbase = q16;
+        qnb1 = Dr * 2; qnb2 = (int64_t)p.n_q * Dr * 2; qnb3 = (int64_t)p.n_head * p.n_q * Dr * 2;
+    }
+    PpArgs pa{};
+    PfArgs& a = pa.f;
+    a.n_q_tiles = (p.n_q + PF_BM - 1) / PF_BM;
+    a.n_kv_tiles = (p.n_kv + PF_BN - 1) / PF_BN;
+    a.n_q_pairs = (a.n_q_tiles + 1) / 2;
+    a.inv_scale = 1.0f / p.scale;
+    a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
+    if (p.mask != nullptr && !p.causal) {
+        uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
+        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2);
+        n++;
+        a.cls = cls;
+        pa.detect_causal = 1;
+    }
+    if (n_seg < 1 || (n_seg > 1 && (part == nullptr || p.Dr != PF_D))) return B200FA_ERR_INVALID;
+    pa.n_seg = n_seg;
+    pa.n_items = a.n_q_pairs * p.n_head * p.n_batch * n_seg;
+    pa.counters = counters;
+    CUtensorMap tq, tk, tv;
+    if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3, 128, Dr)) return B200FA_ERR_CUDA;
+    if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, 128, Dr)) return B200FA_ERR_CUDA;
+    if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, 128, Dr)) return B200FA_ERR_CUDA;
+    CUtensorMap to;
+    {   // dst [batch][n_q][n_head][D]: box = 64 bytes x 1 head x 32 rows, 64-byte swizzle (the epilogue's staging layout)
+        PFN_encodeTiled enc = get_encode_tiled();
+        if (!enc) return B200FA_ERR_CUDA;
+        const bool f32o = n_seg > 1 || p.dst_type == B200FA_TYPE_F32;
+        const cuuint64_t es = f32o ? 4 : 2;
+        const cuuint64_t rowlen = n_seg > 1 ? PF_D + 4 : Dr;  // partial records: O~[D], m, l, 2 unused; dim 3 = segment * n_batch + batch
+        cuuint64_t dims[4] = {rowlen, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch * n_seg};
+        cuuint64_t strides[3] = {rowlen * es, (cuuint64_t)p.n_head * rowlen * es, (cuuint64_t)p.n_q * p.n_head * rowlen * es};
+        cuuint32_t box[4] = {(cuuint32_t)(64 / es), 1, 32, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&to, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, n_seg > 1 ? (void*)part : p.dst, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return B200FA_ERR_CUDA;
+    }
+    constexpr size_t smem_bytes = sizeof(PpShared);
+    static_assert(smem_bytes <= 227 * 1024, "prefill shared memory budget");
+    static const int poly = tune_env("B200FA_POLY") ? atoi(tune_env("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;  // ext2 score modifiers: their own instantiation
+#ifdef B200FA_TUNING
+    auto kern = ext ? fa_prefill_persistent<2, true>
+                    : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));
+    const int ai = ext ? 4 : (poly == 0 ? 0 : (poly == 3 ? 2 : (poly == 4 ? 3 : 1)));
+#else
+    auto kern = ext ? fa_prefill_persistent<2, true> : fa_prefill_persistent<2>;
+    const int ai = ext ? 4 : 1;
+    (void)poly;
+#endif
+    static thread_local bool attr_set[64][5] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev][ai]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
+            return B200FA_ERR_CUDA;
+        attr_set[dev][ai] = true;
+    }
+    const unsigned grid = (unsigned)(pa.n_items < sm_count ? pa.n_items : sm_count);
+    // programmatic dependent launch: the prologue (barrier init, TMEM allocation) may run while the previous kernel of the stream —
+    // the mask classifier, the Q conversion, or the caller's own kernel — is still draining; the kernel waits before its first
+    // global access.
+    static const bool no_pdl = tune_env("B200FA_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PF_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p, pa, tq, tk, tv, to);
+    n++;
+    if (le == cudaSuccess && n_seg > 1) {
+        fa_combine_pad<PF_D><<<(unsigned)p.total_rows, PF_D, 0, st>>>(part, n_seg, p.total_rows, p.dst, p.dst_type, Dr);
+        n++;
+        if (cudaGetLastError() != cudaSuccess) return B200FA_ERR_CUDA;
+    }
+    if (launches) *launches = n;
+    return le == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+
 }  // namespace b200fa

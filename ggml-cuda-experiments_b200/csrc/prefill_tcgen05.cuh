@@ -687,10 +687,13 @@ struct PfDebug {
     float* dump = nullptr;
     int dump_cta = 0;
 };
-inline PfDebug& pf_debug() {
-    static PfDebug d;
-    return d;
-}
+// Diagnostics state (b200fa_debug_set): per calling thread, and only in -DB200FA_TUNING builds — the shipped library keeps no
+// process-global debug state (concurrent calls from several threads share nothing).
+#ifdef B200FA_TUNING
+inline PfDebug& pf_debug() { static thread_local PfDebug d; return d; }
+#else
+inline PfDebug pf_debug() { return PfDebug{}; }
+#endif
 
 inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes, size_t cls_bytes, int sm_count,
                                   cudaStream_t st, int* launches) {
@@ -725,8 +728,12 @@ inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes
     if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13)) return B200FA_ERR_CUDA;
     if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23)) return B200FA_ERR_CUDA;
     constexpr size_t smem_bytes = sizeof(PfShared) + 1024;
-    static const int poly = getenv("B200FA_POLY") ? atoi(getenv("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
+    static const int poly = tune_env("B200FA_POLY") ? atoi(tune_env("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
+#ifdef B200FA_TUNING
     auto kern = poly == 2 ? fa_prefill_tcgen05<2> : (poly == 3 ? fa_prefill_tcgen05<3> : (poly == 4 ? fa_prefill_tcgen05<4> : fa_prefill_tcgen05<0>));
+#else
+    auto kern = fa_prefill_tcgen05<2>;
+#endif
     static thread_local bool attr_set[64][5] = {};
     int dev = 0;
     cudaGetDevice(&dev);

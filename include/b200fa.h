@@ -269,7 +269,9 @@ int b200fa_plan(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne0
 /* Diagnostics: name of the kernel family the last b200fa_flash_attn_ext call on this thread dispatched to
  * ("decode_splitkv", "prefill_tcgen05", "rows16_mma"), and how many kernels it launched. */
 const char* b200fa_last_dispatch(void);
-/* Diagnostics for the tcgen05 kernel: `timeout_word` (8 bytes, device-visible, e.g. mapped host memory) receives a
+/* The two hooks below are INERT in the shipped library: they (and every environment knob) exist only in builds with
+ * -DB200FA_TUNING (ggml-cuda-experiments_b200/build.py build(tuning=True)), where their state is per calling thread.
+ * Diagnostics for the tcgen05 kernel: `timeout_word` (8 bytes, device-visible, e.g. mapped host memory) receives a
  * code if an mbarrier wait times out (the kernel then traps instead of hanging); `dump` (device, (2*128*128+256) f32)
  * receives the first raw score tile, the unnormalised output tile and (l, m) of CTA `dump_cta`.  NULL disables. */
 void b200fa_debug_set(void* timeout_word, float* dump, int dump_cta);

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
+from parity_log import three_way
 from common import assert_close, load_ref_host_cases, make_mask, synth_qkv
 from gpu_common import kv_cache_view, pkg, run_both, to_dev
 
@@ -184,13 +185,13 @@ def test_vs_reference_cuda_flash_attn_row(n_kv):
     torch.cuda.synchronize()
     assert rc == 0
     refgpu = dst.cpu().numpy()
-    e_ref = np.abs(refgpu - ref32[0, 0]).max()
-    e_new = np.abs(ours[0, 0] - ref32[0, 0]).max()
-    e_x = np.abs(ours[0, 0] - refgpu).max()
-    print(f"n_kv={n_kv}: ours-fp32 {e_new:.2e}  refgpu-fp32 {e_ref:.2e}  ours-refgpu {e_x:.2e}")
-    # gate ours-vs-refgpu only where the f16-accumulating reference is itself inside tolerance
-    if np.all(np.abs(refgpu - ref32[0, 0]) <= 2e-3 + 1e-2 * np.abs(ref32[0, 0])):
-        assert_close(ours[0, 0], refgpu, "ours vs reference CUDA", atol=4e-3, rtol=2e-2)
+    e, ref_ok = three_way(f"flash_attn_row+fa_reduce n_kv={n_kv} (32q/8kv, noise mask)", ours[0, 0], refgpu, ref32[0, 0],
+                          note="flash_row_float.h:4-200,415-472 vs b200fa vs fp32 oracle, kernel_test.h recipe")
+    # ours is always held to the oracle (run_both asserted it); ours-vs-refgpu is only a meaningful gate where the f16-accumulating
+    # reference kernel is itself inside the tolerance — otherwise say so loudly instead of passing having compared nothing
+    if not ref_ok:
+        pytest.skip(f"reference kernel outside tolerance on this input: {e}")
+    assert_close(ours[0, 0], refgpu, "ours vs reference CUDA", atol=4e-3, rtol=2e-2)
 
 
 def test_vs_reference_cuda_flash_attn_ext_f16_decode():
@@ -212,10 +213,11 @@ def test_vs_reference_cuda_flash_attn_ext_f16_decode():
     torch.cuda.synchronize()
     assert rc == 0
     refgpu = dst.cpu().numpy()
-    print(f"ext_f16: ours-fp32 {np.abs(ours[0,0]-ref32[0,0]).max():.2e} refgpu-fp32 {np.abs(refgpu-ref32[0,0]).max():.2e} "
-          f"ours-refgpu {np.abs(ours[0,0]-refgpu).max():.2e}")
-    if np.all(np.abs(refgpu - ref32[0, 0]) <= 2e-3 + 1e-2 * np.abs(ref32[0, 0])):
-        assert_close(ours[0, 0], refgpu, "ours vs reference CUDA ext_f16", atol=4e-3, rtol=2e-2)
+    e, ref_ok = three_way("flash_attn_ext_f16 decode n_kv=512 (32q/8kv, noise mask)", ours[0, 0], refgpu, ref32[0, 0],
+                          note="flash-llama.h:5-438 launched as kernel_test.h:191-198")
+    if not ref_ok:
+        pytest.skip(f"reference kernel outside tolerance on this input: {e}")
+    assert_close(ours[0, 0], refgpu, "ours vs reference CUDA ext_f16", atol=4e-3, rtol=2e-2)
 
 
 def test_error_paths_on_device():

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
+from parity_log import three_way
 from common import assert_close, make_mask, synth_qkv
 from gpu_common import pkg, run_both, to_dev
 
@@ -149,10 +150,11 @@ def test_vs_reference_cuda_flash_attn_ext_f16_prefill():
     torch.cuda.synchronize()
     assert rc == 0
     refgpu = dst.cpu().numpy()
-    print(f"prefill: ours-fp32 {np.abs(ours[0]-ref32[0]).max():.2e} refgpu-fp32 {np.abs(refgpu-ref32[0]).max():.2e} "
-          f"ours-refgpu {np.abs(ours[0]-refgpu).max():.2e}")
-    if np.all(np.abs(refgpu - ref32[0]) <= 2e-3 + 1e-2 * np.abs(ref32[0])):
-        assert_close(ours[0], refgpu, "ours vs reference CUDA prefill", atol=4e-3, rtol=2e-2)
+    e, ref_ok = three_way("flash_attn_ext_f16 prefill 128x256 (4q/2kv, noise mask)", ours[0], refgpu, ref32[0],
+                          note="flash-llama.h:5-438 launched as flash-matrix.cu:198-206")
+    if not ref_ok:
+        pytest.skip(f"reference kernel outside tolerance on this input: {e}")
+    assert_close(ours[0], refgpu, "ours vs reference CUDA prefill", atol=4e-3, rtol=2e-2)
 
 
 # ---- persistent scheduler: more work items than SMs, uneven item costs, odd tile counts, batches ----
