@@ -69,8 +69,14 @@ def lib() -> C.CDLL:
         l.b200fa_peer_close.argtypes = [vp]
         l.b200fa_peer_free.restype = C.c_int
         l.b200fa_peer_free.argtypes = [vp]
+        l.b200fa_peer_set_timeout.restype = C.c_int
+        l.b200fa_peer_set_timeout.argtypes = [vp, C.c_int, vp]
+        l.b200fa_peer_status.restype = C.c_int
+        l.b200fa_peer_status.argtypes = [vp, C.POINTER(C.c_int), vp]
+        l.b200fa_peer_reset.restype = C.c_int
+        l.b200fa_peer_reset.argtypes = [vp, vp]
         l.b200fa_kv_cache_append.restype = C.c_int
-        l.b200fa_kv_cache_append.argtypes = [vp, C.c_int, vp, C.c_int] + [i64] * 11 + [vp]
+        l.b200fa_kv_cache_append.argtypes = [vp, C.c_int, vp, C.c_int] + [i64] * 12 + [vp]
         l.b200fa_debug_timeline.restype = None
         l.b200fa_debug_timeline.argtypes = [vp]
         _lib = l
@@ -113,6 +119,30 @@ def _type_of(t, explicit=None) -> int:
 
 def workspace_size(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, flags=0) -> int:
     return lib().b200fa_workspace_size(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, flags)
+
+
+def _temp_workspace(nbytes, device, stream):
+    """Scratch for a call that was given none.  The launch is asynchronous and the wrapper drops the buffer on return: that is
+    only safe on the allocating (current) stream, so for any other stream the caching allocator is told about the use."""
+    import torch
+    ws = Workspace(nbytes, device)
+    if stream is not None and stream != torch.cuda.current_stream(device):
+        ws.buf.record_stream(stream)
+    return ws
+
+
+class _on_device_of:
+    """The C side enqueues on the CURRENT device: make that the device of the tensors for the duration of the call."""
+
+    def __init__(self, t):
+        import torch
+        self.g = torch.cuda.device(t.device)
+
+    def __enter__(self):
+        return self.g.__enter__()
+
+    def __exit__(self, *a):
+        return self.g.__exit__(*a)
 
 
 class Workspace:
@@ -187,9 +217,10 @@ def flash_attn_ext(q, k, v, mask=None, scale=None, dst=None, dst_dtype=None, fla
         dst = torch.empty((n_b, n_q, n_head, D), dtype=dst_dtype or torch.float32, device=q.device)
     dt = _type_of(dst)
     if workspace is None:
-        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+        workspace = _temp_workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device, stream)
     m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
-    rc = flash_attn_ext_raw(q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, dt,
+    with _on_device_of(q):
+        rc = flash_attn_ext_raw(q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, dt,
                             q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb, flags, workspace.ptr, workspace.nbytes,
                             _stream_ptr(stream), max_bias, logit_softcap)
     if rc != 0:
@@ -211,9 +242,10 @@ def flash_attn_partial(q, k, v, mask=None, scale=None, kv_pos0=0, n_kv_total=Non
     if out is None:
         out = torch.empty((n_b * n_q * n_head, D + 2), dtype=torch.float32, device=q.device)
     if workspace is None:
-        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+        workspace = _temp_workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device, stream)
     m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
-    rc = lib().b200fa_flash_attn_partial(
+    with _on_device_of(q):
+        rc = lib().b200fa_flash_attn_partial(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, out.data_ptr(), scale, qt, kt, *q_ne, *k_ne, ne31, nb31,
         q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
         flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
@@ -268,7 +300,7 @@ def kv_cache_append(src, cache, n_past: int, cache_type=None, stream=None):
     rc = lib().b200fa_kv_cache_append(
         src.data_ptr(), st, cache.data_ptr(), ct, D, n_tok, n_hk, n_b,
         src.stride(1) * es, src.stride(2) * es, src.stride(0) * es,
-        cache.stride(2) * ces, cache.stride(1) * ces, cache.stride(0) * ces, n_past, _stream_ptr(stream))
+        cache.stride(2) * ces, cache.stride(1) * ces, cache.stride(0) * ces, n_past, cache.shape[2], _stream_ptr(stream))
     if rc != 0:
         raise B200FAError(rc, "b200fa_kv_cache_append")
     return cache
@@ -280,9 +312,10 @@ class PeerExchange:
     `PeerExchange.distributed(rows, D, group)` allocates this rank's buffer, exchanges cudaIpc handles through
     torch.distributed and maps every peer's buffer (one process per GPU on one node)."""
 
-    def __init__(self, world, rank, rows, D, own_ptr, peer_ptrs, owned, opened):
+    def __init__(self, world, rank, rows, D, own_ptr, peer_ptrs, owned, opened, single_device=False):
         import torch
         self.world, self.rank, self.rows, self.D = world, rank, rows, D
+        self.single_device = single_device  # all ranks' buffers live on one device (local()): the fused one-kernel step cannot run
         self.own_ptr, self.peer_ptrs, self._owned, self._opened = own_ptr, list(peer_ptrs), owned, opened
         self.peers_dev = torch.tensor(self.peer_ptrs, dtype=torch.int64, device="cuda")  # device array of pointers
 
@@ -292,7 +325,10 @@ class PeerExchange:
 
     @classmethod
     def local(cls, world, rows, D):
-        """`world` buffers on the current device; returns one PeerExchange per emulated rank."""
+        """`world` buffers on the current device; returns one PeerExchange per emulated rank.
+        Only the launch-separated protocol works on such an exchange (flash_attn_partial_scatter by every rank FIRST, then
+        merge_partials_wait): a kernel that waits for a peer's kernel queued behind it on the same device never sees it arrive,
+        so flash_attn_seqpar refuses an emulated exchange with world > 1."""
         ptrs, handles = [], []
         for _ in range(world):
             p = C.c_void_p(); h = C.create_string_buffer(64)
@@ -300,7 +336,7 @@ class PeerExchange:
             if rc != 0:
                 raise B200FAError(rc, "b200fa_peer_alloc")
             ptrs.append(p.value)
-        return [cls(world, r, rows, D, ptrs[r], ptrs, owned=[ptrs[r]], opened=[]) for r in range(world)]
+        return [cls(world, r, rows, D, ptrs[r], ptrs, owned=[ptrs[r]], opened=[], single_device=True) for r in range(world)]
 
     @classmethod
     def distributed(cls, rows, D, group=None):
@@ -324,6 +360,26 @@ class PeerExchange:
                 ptrs.append(q.value); opened.append(q.value)
         return cls(world, rank, rows, D, p.value, ptrs, owned=[p.value], opened=opened)
 
+    def set_timeout(self, ms: int, stream=None):
+        """Timeout of the device-side waits on this rank's buffer (default 4 s); a timed-out wait raises the error flag, never traps."""
+        rc = lib().b200fa_peer_set_timeout(self.own_ptr, int(ms), _stream_ptr(stream))
+        if rc != 0:
+            raise B200FAError(rc, "b200fa_peer_set_timeout")
+
+    def timed_out(self, stream=None) -> bool:
+        """True if a wait on this rank's buffer timed out since the last reset (synchronises the stream)."""
+        flag = C.c_int(0)
+        rc = lib().b200fa_peer_status(self.own_ptr, C.byref(flag), _stream_ptr(stream))
+        if rc != 0:
+            raise B200FAError(rc, "b200fa_peer_status")
+        return bool(flag.value)
+
+    def reset(self, stream=None):
+        """Back to step 0 (call on EVERY rank at the same point, e.g. after a step that timed out or returned an error somewhere)."""
+        rc = lib().b200fa_peer_reset(self.own_ptr, _stream_ptr(stream))
+        if rc != 0:
+            raise B200FAError(rc, "b200fa_peer_reset")
+
     def close(self):
         for q in self._opened:
             lib().b200fa_peer_close(q)
@@ -343,9 +399,10 @@ def flash_attn_partial_scatter(q, k, v, xch: PeerExchange, mask=None, scale=None
     if n_kv_total is None:
         n_kv_total = kv_pos0 + k_ne[1]
     if workspace is None:
-        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+        workspace = _temp_workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device, stream)
     m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
-    rc = lib().b200fa_flash_attn_partial_scatter(
+    with _on_device_of(q):
+        rc = lib().b200fa_flash_attn_partial_scatter(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, scale, qt, kt, *q_ne, *k_ne, ne31, nb31,
         q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
         xch.own_ptr, xch.peers_dev.data_ptr(), xch.rank, xch.world, flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
@@ -368,6 +425,9 @@ def flash_attn_seqpar(q, k, v, xch: PeerExchange, mask=None, scale=None, kv_pos0
                       workspace: Workspace | None = None, stream=None, kv_type=None):
     """One sequence-parallel step in one call (one kernel for decode shapes): this rank's KV band -> dst [rows][D] on every rank."""
     import torch
+    if xch.single_device and xch.world > 1:
+        raise B200FAError(-2, "flash_attn_seqpar on an exchange emulated on one device (PeerExchange.local): the ranks' kernels cannot "
+                              "run concurrently there; use flash_attn_partial_scatter + merge_partials_wait")
     qt, kt = _type_of(q), _type_of(k, kv_type)
     q_ne, q_nb = _ne_nb(q, qt); k_ne, k_nb = _ne_nb(k, kt); _, v_nb = _ne_nb(v, kt)
     D, n_q, n_head, n_b = q_ne
@@ -378,9 +438,10 @@ def flash_attn_seqpar(q, k, v, xch: PeerExchange, mask=None, scale=None, kv_pos0
     if dst is None:
         dst = torch.empty((n_b * n_q * n_head, D), dtype=dst_dtype or torch.float32, device=q.device)
     if workspace is None:
-        workspace = Workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device)
+        workspace = _temp_workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device, stream)
     m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
-    rc = lib().b200fa_flash_attn_seqpar(
+    with _on_device_of(q):
+        rc = lib().b200fa_flash_attn_seqpar(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, _type_of(dst), *q_ne, *k_ne, ne31, nb31,
         q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
         xch.own_ptr, xch.peers_dev.data_ptr(), xch.rank, xch.world, flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))

@@ -86,6 +86,14 @@ struct Shape {
     bool ext = false;  // ALiBi / soft-cap requested (ext2 entry): only the persistent prefill kernel implements them
 };
 
+// The one place a call's arguments become the planner's view of it (attn_common, b200fa_flash_attn_seqpar and b200fa_plan agree by
+// construction): D is the structural head size of the decode kernels (64 or 128), Dr the real one.
+Shape make_shape(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03, int64_t ne11, int64_t ne12, int64_t ne13,
+                 int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23, const void* k, const void* v,
+                 int64_t kv_pos0, int64_t n_kv_total) {
+    return Shape{q_type, kv_type, ne00 <= 64 ? 64 : 128, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
+}
+
 bool stream_eligible(const Shape& sh, bool sizing) {
     const int64_t rows = sh.n_q * (sh.n_head / sh.n_head_kv);
     if (rows > 16 || (sh.D != 64 && sh.D != 128)) return false;
@@ -509,7 +517,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     const int64_t Dp = ne00 <= 64 ? 64 : 128;  // structural head size of the decode kernels; the prefill kernel is always 128 wide
     const float max_bias = ext ? ext->max_bias : 0.f, softcap = ext ? ext->logit_softcap : 0.f;
     if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
-    Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
+    Shape sh = make_shape(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total);
     sh.ext = max_bias > 0.f || softcap != 0.f;
     // 17..128 rows per KV head from a GQA group (a burst of up to 16 query positions, e.g. speculative decoding): split every real
     // KV head into kv_div VIRTUAL heads of gqa / kv_div q heads each, so that a unit has <= 16 rows and the stream kernel applies.
@@ -574,7 +582,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
             p.nb11 = p.nb21 = ne00 * 2; p.nb12 = p.nb22 = ne11 * ne00 * 2; p.nb13 = p.nb23 = ne12 * ne11 * ne00 * 2;
         }
         static const bool per_cta = tune_env("B200FA_PREFILL") && !strcmp(tune_env("B200FA_PREFILL"), "cta");
-        if ((per_cta && p.Dr == PF_D) || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
+        if ((per_cta && p.Dr == PF_D && !sh.ext) || ne11 > (int64_t)PP_MAX_KV_TILES * PF_BN) {
             rc = launch_prefill_tcgen05(p, ws + pl.ctr_bytes, pl.qf16_bytes, pl.cls_bytes, di.sm_count, st, &launches);
         } else {
             if (!(flags & B200FA_FLAG_WORKSPACE_ZEROED) && cudaMemsetAsync(ws + kPrefillCtrOff, 0, 256, st) != cudaSuccess) return B200FA_ERR_CUDA;
@@ -590,6 +598,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (pl.n_counters > 0 && (!(flags & B200FA_FLAG_WORKSPACE_ZEROED) || pl.ctr_bytes != kCtrRegion)) {
         if (cudaMemsetAsync(ws, 0, align_up(pl.n_counters * 4, 256), st) != cudaSuccess) return B200FA_ERR_CUDA;
     }
+    if (g_seqpar.peers != nullptr && pl.kind != kStream) return B200FA_ERR_UNSUPPORTED;  // the fused step exists in the stream kernel only
     if (pl.kind == kStream) {
         if (kv_div > 1) { p.kv_div = kv_div; p.n_head_kv = (int)ne12 * kv_div; p.gqa = (int)(ne02 / ne12) / kv_div; }
         g_last_dispatch = want_partial ? "decode_stream_partial" : "decode_stream";
@@ -720,7 +729,12 @@ int b200fa_flash_attn_seqpar(const void* q, const void* k, const void* v, const 
     // one launch when the stream decode kernel takes the shape; otherwise the three-launch sequence
     const DeviceInfo& di = device_info();
     if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;
-    Shape sh{q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total};
+    {   // the same argument checks attn_common applies, BEFORE any planning arithmetic (ne12 = 0 must be an error, not a division)
+        const int rcv = validate(q, k, v, (char*)xchg + kXchgHeader, q_type, kv_type, B200FA_TYPE_F32, ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13,
+                                 mask, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, true);
+        if (rcv != B200FA_OK) return rcv;
+    }
+    const Shape sh = make_shape(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total);
     const Plan pl = make_plan(sh, flags, di.sm_count, true, false);
     if (pl.kind == kStream) {
         float* staging = reinterpret_cast<float*>((char*)xchg + kXchgHeader);  // never written in this mode; only a non-null partial_out
@@ -768,6 +782,24 @@ int b200fa_peer_open(const unsigned char handle[64], void** ptr) {
     memcpy(&h, handle, 64);
     return cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
+int b200fa_peer_set_timeout(void* xchg, int timeout_ms, b200fa_stream_t stream) {
+    if (!xchg || timeout_ms < 0) return B200FA_ERR_INVALID;
+    fa_xchg_set_word<<<1, 1, 0, (cudaStream_t)stream>>>((char*)xchg, kXchgTimeoutWord, (unsigned int)timeout_ms);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
+int b200fa_peer_status(const void* xchg, int* timed_out, b200fa_stream_t stream) {
+    if (!xchg || !timed_out) return B200FA_ERR_INVALID;
+    unsigned int w = 0;
+    if (cudaMemcpyAsync(&w, (const char*)xchg + kXchgErrWord * 4, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return B200FA_ERR_CUDA;
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return B200FA_ERR_CUDA;
+    *timed_out = w != 0u;
+    return B200FA_OK;
+}
+int b200fa_peer_reset(void* xchg, b200fa_stream_t stream) {
+    if (!xchg) return B200FA_ERR_INVALID;
+    fa_xchg_reset<<<1, kXchgHeader / 4, 0, (cudaStream_t)stream>>>((char*)xchg);
+    return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+}
 int b200fa_peer_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA; }
 int b200fa_peer_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA; }
 
@@ -810,8 +842,10 @@ int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n, b200fa_stream
 
 int b200fa_kv_cache_append(const void* src, int src_type, void* cache, int cache_type, int64_t D, int64_t n_tokens, int64_t n_head_kv,
                            int64_t n_batch, int64_t src_nb1, int64_t src_nb2, int64_t src_nb3, int64_t cache_nb1, int64_t cache_nb2,
-                           int64_t cache_nb3, int64_t n_past, b200fa_stream_t stream) {
-    if (!src || !cache || D <= 0 || D % 32 || n_tokens <= 0 || n_head_kv <= 0 || n_batch <= 0 || n_past < 0) return B200FA_ERR_INVALID;
+                           int64_t cache_nb3, int64_t n_past, int64_t n_kv_max, b200fa_stream_t stream) {
+    if (!src || !cache || D <= 0 || n_tokens <= 0 || n_head_kv <= 0 || n_batch <= 0 || n_past < 0) return B200FA_ERR_INVALID;
+    if (D % (cache_type == B200FA_TYPE_Q8_0 ? 32 : 8)) return B200FA_ERR_INVALID;  // the head sizes the attention entries take for that cache type
+    if (n_kv_max <= 0 || n_past + n_tokens > n_kv_max) return B200FA_ERR_INVALID;   // the rows would land past the end of the cache
     if (src_type != B200FA_TYPE_F32 && src_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
     if (cache_type != B200FA_TYPE_F16 && cache_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
     const int64_t es = src_type == B200FA_TYPE_F32 ? 4 : 2;

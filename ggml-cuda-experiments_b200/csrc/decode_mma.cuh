@@ -741,11 +741,45 @@ __global__ void __launch_bounds__(D) fa_combine_pad(const float* __restrict__ pa
 //   gathered  [gen][rank][row][D + 2] f32 : two generations (step parity)
 // The step number lives on the device, so a step is a fixed sequence of launches that can be captured in a CUDA graph.
 constexpr int kXchgHeader = 256;
+// header words (u32): [0] arrivals of all ranks (monotonic), [16] [17] local block counters, [32] steps completed on this rank,
+// [33] error flag: 1 = a wait for the peers timed out (the step's output was NOT written; b200fa_peer_status / b200fa_peer_reset),
+// [34] timeout of those waits in milliseconds (0 = kXchgDefaultTimeoutMs; b200fa_peer_set_timeout)
+constexpr int kXchgErrWord = 33, kXchgTimeoutWord = 34;
+constexpr unsigned int kXchgDefaultTimeoutMs = 4000;
+
+__device__ __forceinline__ unsigned long long xchg_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// One thread waits (system-scope acquire loads) until all ranks' arrivals of step `want / n` are in.  Returns false after the
+// exchange's timeout — a missing, late or failed rank — having raised the header's error flag: the caller then SKIPS its merge and
+// the kernel ends normally (no trap: a trap leaves a sticky context error on every rank for what may be a few seconds of skew).
+__device__ __forceinline__ bool xchg_wait_arrivals(unsigned int* hdr, unsigned int want);
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ bool xchg_wait_arrivals(unsigned int* hdr, unsigned int want) {
+    if ((int)(ld_acquire_sys(hdr) - want) >= 0) return true;
+    const unsigned int ms = hdr[kXchgTimeoutWord] ? hdr[kXchgTimeoutWord] : kXchgDefaultTimeoutMs;
+    const unsigned long long t0 = xchg_now_ns(), limit = (unsigned long long)ms * 1000000ull;
+    while ((int)(ld_acquire_sys(hdr) - want) < 0) {
+        if (xchg_now_ns() - t0 > limit) {
+            atomicExch(hdr + kXchgErrWord, 1u);
+            return false;
+        }
+    }
+    return true;
+}
+__global__ void fa_xchg_set_word(char* xchg, int word, unsigned int value) { reinterpret_cast<unsigned int*>(xchg)[word] = value; }
+// header back to its initial state (steps, arrivals, counters, error flag), keeping the configured timeout
+__global__ void fa_xchg_reset(char* xchg) {
+    unsigned int* hdr = reinterpret_cast<unsigned int*>(xchg);
+    if (threadIdx.x < kXchgHeader / 4 && threadIdx.x != kXchgTimeoutWord) hdr[threadIdx.x] = 0u;
 }
 
 // Copies this rank's staged triples into slot `rank` of every rank's gathered area (its own included) with plain stores —
@@ -775,14 +809,10 @@ template <int D>
 __global__ void __launch_bounds__(D) fa_combine_wait(char* __restrict__ xchg, int n_parts, int64_t n_rows, void* __restrict__ dst, int dst_type) {
     unsigned int* hdr = reinterpret_cast<unsigned int*>(xchg);
     const unsigned int step = hdr[32] + 1;
-    if (threadIdx.x == 0) {
-        const unsigned int want = step * (unsigned int)n_parts;
-        const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(hdr) - want) < 0) {
-            if (clock64() - t0 > 8000000000LL) __trap();  // a missing rank must not hang the GPU
-        }
-    }
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = xchg_wait_arrivals(hdr, step * (unsigned int)n_parts) ? 1 : 0;
     __syncthreads();
+    if (!s_ok) return;  // timed out: error flag raised, dst untouched, the step is not counted (b200fa_peer_reset)
     const int64_t n_floats = n_rows * (D + 2);
     const float* part = reinterpret_cast<const float*>(xchg + kXchgHeader) + n_floats + (int64_t)(step & 1u) * n_parts * n_floats;
     const int64_t row = blockIdx.x;

@@ -806,13 +806,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 for (int pr = 0; pr < a.world; pr++) atomicAdd_system(reinterpret_cast<unsigned int*>(a.peers[pr]), 1u);
             }
             // every publishing CTA waits for all ranks' arrivals, then merges its share of the output (fa_reduce algebra)
-            const unsigned int want = sp_step * (unsigned int)a.world;
-            const long long t0 = clock64();
-            while ((int)(ld_acquire_sys(hdr) - want) < 0) {
-                if (clock64() - t0 > 8000000000LL) __trap();  // a missing rank must not hang the GPU
-            }
+            s_flag[3] = xchg_wait_arrivals(hdr, sp_step * (unsigned int)a.world) ? 1 : 0;
         }
         bar_consumers();
+        if (s_flag[3] == 0) return;  // timed out (error flag raised in the header): no merge, no step count; the kernel ends normally
         const int64_t n_out = p.total_rows * D;
         const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;  // share ~ units published
         const float* part = reinterpret_cast<const float*>(a.peers[a.rank] + kXchgHeader) + sp_n_floats + sp_gen_off;

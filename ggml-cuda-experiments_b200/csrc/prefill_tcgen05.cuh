@@ -38,7 +38,12 @@ constexpr uint32_t PF_TILE_BYTES = 128 * 128 * 2;  // one 128x128 f16 tile
 constexpr uint32_t PF_TMEM_COLS = 512;
 constexpr uint32_t PF_TM_S = 0, PF_TM_O = 256;     // tile t: S at PF_TM_S + 128*t, O at PF_TM_O + 128*t
 constexpr float PF_RESCALE_THRESHOLD = 8.0f;       // log2 units
-constexpr int PF_REGS_SOFTMAX = 216, PF_REGS_OTHER = 40;
+#ifndef B200FA_PF_REGS_OTHER
+#define B200FA_PF_REGS_OTHER 72
+#endif
+// 2 x 128 x 216 + 128 x 72 registers = 63 K of the 64 K file (80 would fill it exactly: the launch fails).  At 40 the MMA issuers
+// spilled their descriptors inside the issue loop.
+constexpr int PF_REGS_SOFTMAX = 216, PF_REGS_OTHER = B200FA_PF_REGS_OTHER;
 constexpr int PF_STAGGER_CYCLES = 500;
 constexpr int PF_MAX_KV_TILES = 4096;              // schedule capacity: n_kv <= 524288 on this path
 

@@ -48,12 +48,15 @@ __global__ void kv_append_kernel(const char* __restrict__ src, char* __restrict_
     const int64_t b = row / ((int64_t)n_tokens * n_head_kv);
     const T* x = reinterpret_cast<const T*>(src + tok * snb1 + head * snb2 + b * snb3);
     char* dst = cache + (n_past + tok) * cnb1 + head * cnb2 + b * cnb3;
-    for (int blk = 0; blk < D / 32; blk++) {
-        float v;
-        if constexpr (sizeof(T) == 2) v = __half2float(x[blk * 32 + lane]);
-        else v = x[blk * 32 + lane];
+    for (int blk = 0; blk < (D + 31) / 32; blk++) {
+        const bool in = blk * 32 + lane < D;  // f16 caches take any head size (multiple of 8); q8_0 rows are whole 32-element blocks
+        float v = 0.f;
+        if (in) {
+            if constexpr (sizeof(T) == 2) v = __half2float(x[blk * 32 + lane]);
+            else v = x[blk * 32 + lane];
+        }
         if (cache_type == B200FA_TYPE_F16) {
-            reinterpret_cast<__half*>(dst)[blk * 32 + lane] = __float2half_rn(v);
+            if (in) reinterpret_cast<__half*>(dst)[blk * 32 + lane] = __float2half_rn(v);
         } else {
             float amax = fabsf(v);
 #pragma unroll

@@ -173,7 +173,12 @@ int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, in
  *        own exchange buffer and are then stored into the same slot of every peer's buffer (plain NVLink stores), followed
  *        by a system-scope fence and one atomic increment of each peer's arrival counter;
 *   b200fa_merge_partials_wait        : waits (on the device) until all `world` ranks have published this step, then merges
- *        (fa_reduce algebra) into dst.  Bounded wait: traps after ~4 s instead of hanging.
+ *        (fa_reduce algebra) into dst.  The wait is BOUNDED and never traps: after the exchange's timeout (b200fa_peer_set_timeout,
+ *        default 4 s) the kernel raises the buffer's error flag, skips the merge (dst is left untouched, the step is not counted)
+ *        and ends normally — poll b200fa_peer_status, and b200fa_peer_reset on every rank before using the exchange again.
+ * The ranks' kernels must be able to run AT THE SAME TIME: one rank per device.  Several ranks on one device cannot
+ * (a kernel that waits for a peer launched behind it never sees it arrive; B200_PROFILING.md) — emulate them with the plain
+ * b200fa_flash_attn_partial + b200fa_merge_partials pair instead.
  * Two generations of the gathered area (step parity) make it safe for a fast rank to start the next step early.
  */
 size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D);
@@ -210,6 +215,12 @@ int b200fa_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
 int b200fa_peer_open(const unsigned char handle[64], void** ptr);
 int b200fa_peer_close(void* ptr);
 int b200fa_peer_free(void* ptr);
+/* Timeout (ms, 0 = the 4 s default) of the device-side waits on this rank's exchange buffer; error flag raised by a timed-out wait
+ * (this call synchronises `stream`); header back to step 0 (arrivals, counters, error flag — the timeout is kept): to be called by
+ * EVERY rank at the same point of the protocol, after a step that failed or timed out on any of them. */
+int b200fa_peer_set_timeout(void* xchg, int timeout_ms, b200fa_stream_t stream);
+int b200fa_peer_status(const void* xchg, int* timed_out, b200fa_stream_t stream);
+int b200fa_peer_reset(void* xchg, b200fa_stream_t stream);
 
 /*
  * ggml q8_0 rows (block {f16 d; int8 qs[32]}, 34 bytes).  Not in the reference;
@@ -225,11 +236,13 @@ int b200fa_dequantize_q8_0(const void* src, float* dst, int64_t n_elements, b200
  * converting f32/f16 -> f16 or -> q8_0 blocks on the way.  Replaces the host-side repacking loops of the reference's driver
  * (flash-matrix.cu:130-165).  src element (d, tok, head, b) at src + tok*src_nb1 + head*src_nb2 + b*src_nb3 (+ d*elem);
  * cache row (n_past + tok, head, b) at cache + (n_past+tok)*cache_nb1 + head*cache_nb2 + b*cache_nb3 — the same nb the
- * attention entry takes for that tensor.  D % 32 == 0.
+ * attention entry takes for that tensor.  D: a multiple of 8 for an f16 cache, of 32 for q8_0 (the head sizes the attention entries
+ * accept for that cache type).  n_kv_max: rows the cache holds per (head, batch); n_past + n_tokens > n_kv_max is B200FA_ERR_INVALID.
  */
 int b200fa_kv_cache_append(const void* src, int src_type, void* cache, int cache_type, int64_t D, int64_t n_tokens,
                            int64_t n_head_kv, int64_t n_batch, int64_t src_nb1, int64_t src_nb2, int64_t src_nb3,
-                           int64_t cache_nb1, int64_t cache_nb2, int64_t cache_nb3, int64_t n_past, b200fa_stream_t stream);
+                           int64_t cache_nb1, int64_t cache_nb2, int64_t cache_nb3, int64_t n_past, int64_t n_kv_max,
+                           b200fa_stream_t stream);
 
 /*
  * ggml tensor-dump files (host side, no GPU involved): the fixture format the reference replays

@@ -392,3 +392,76 @@ def test_gqa_bursts_17_to_64_rows_use_the_stream_kernel(n_q, H, Hk, B, n_kv, kin
     run_both(Q, K, V, mask, flags=flags, q8=q8, mask_pad=32 if mask is not None else None)
     assert pkg().last_dispatch() == "decode_stream", pkg().last_dispatch()
     a, _ = run_both(Q, K, V, mask, flags=flags, q8=q8, cache_view=not q8, dst_f16=True)
+
+
+def test_kv_cache_append_bounds_and_padded_head_sizes():
+    """appending past the end of the cache is an error (not an out-of-bounds write), and an f16 cache takes every head
+    size the attention entries take (multiples of 8), e.g. 80."""
+    import torch
+    P = pkg()
+    B, Hk, n_max = 2, 3, 64
+    for D in (80, 128):
+        cache = torch.zeros((B, Hk, n_max, D), dtype=torch.float16, device="cuda")
+        guard = cache.clone()
+        src = (torch.rand((B, 10, Hk, D), device="cuda") * 2 - 1)
+        P.kv_cache_append(src, cache, 54)   # rows 54..63: exactly fits
+        torch.cuda.synchronize()
+        assert torch.equal(cache[:, :, 54:64], src.permute(0, 2, 1, 3).half())
+        assert torch.equal(cache[:, :, :54], guard[:, :, :54])
+        with pytest.raises(P.B200FAError):
+            P.kv_cache_append(src, cache, 55)   # one row too many
+    q8 = torch.zeros((B, Hk, n_max, 80 // 32 * 34), dtype=torch.uint8, device="cuda")
+    with pytest.raises(P.B200FAError):  # q8_0 rows are whole 32-element blocks: 80 is not a q8_0 head size
+        P.kv_cache_append(torch.zeros((B, 1, Hk, 80), device="cuda"), q8, 0, cache_type=P.TYPE_Q8_0)
+
+
+def test_seqpar_argument_errors_and_emulated_exchange():
+    """b200fa_flash_attn_seqpar validates before it plans (ne12 = 0 used to be a division by zero), and the fused
+    one-kernel step refuses an exchange whose ranks live on one device (it could only dead-lock there)."""
+    import ctypes as C
+    import torch
+    P = pkg()
+    xs = P.PeerExchange.local(2, 32, 128)
+    q = torch.zeros((1, 32, 1, 128), device="cuda"); k = torch.zeros((1, 8, 256, 128), dtype=torch.float16, device="cuda")
+    with pytest.raises(P.B200FAError):
+        P.flash_attn_seqpar(q, k, k, xs[0], kv_pos0=0, n_kv_total=512)
+    ws = P.Workspace(1 << 20)
+    x1 = P.PeerExchange.local(1, 32, 128)[0]
+    args = [q.data_ptr(), k.data_ptr(), k.data_ptr(), None, q.data_ptr(), C.c_float(0.1), 0, 1, 0,
+            128, 1, 32, 1, 128, 256, 0, 1,   # ne12 = 0
+            0, 0, 512, 512, 16384, 256, 65536, 524288, 256, 65536, 524288, 0, 256,
+            x1.own_ptr, x1.peers_dev.data_ptr(), 0, 1, 0, ws.ptr, ws.nbytes, None]
+    assert P.lib().b200fa_flash_attn_seqpar(*args) == -1
+    for x in xs + [x1]:
+        x.close()
+
+
+def test_peer_exchange_timeout_raises_a_flag_instead_of_a_trap():
+    """a wait for peers that never arrive ends after the configured timeout with the exchange's error flag raised and a
+    healthy context; after b200fa_peer_reset the exchange works again."""
+    import torch
+    P = pkg()
+    D, rows = 128, 32
+    xs = P.PeerExchange.local(2, rows, D)   # rank 1 never publishes
+    Q, K, V = synth_qkv(D, 1, 512, 32, 8)
+    q, k, v = to_dev(Q), to_dev(K), to_dev(V)
+    xs[0].set_timeout(50)
+    dst = torch.full((rows, D), 7.0, device="cuda")
+    P.flash_attn_partial_scatter(q, k, v, xs[0], kv_pos0=0, n_kv_total=1024)
+    P.merge_partials_wait(xs[0], dst=dst)
+    torch.cuda.synchronize()            # no sticky error: the kernel ended normally
+    assert xs[0].timed_out() and not xs[1].timed_out()
+    assert float(dst.min()) == 7.0      # dst untouched
+    for x in xs:
+        x.reset()
+    assert not xs[0].timed_out()
+    # a complete step on the reset exchange: both emulated ranks publish, then both merge
+    ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), None, 1 / np.sqrt(D), round_q_f16=True)
+    for r in range(2):
+        P.flash_attn_partial_scatter(q, k[:, :, r * 256:(r + 1) * 256], v[:, :, r * 256:(r + 1) * 256], xs[r], kv_pos0=r * 256, n_kv_total=512)
+    for r in range(2):
+        out = P.merge_partials_wait(xs[r])
+        torch.cuda.synchronize()
+        assert_close(out.cpu().numpy().reshape(ref.shape), ref, f"after reset, rank {r}")
+    for x in xs:
+        x.close()

@@ -50,3 +50,36 @@ def test_replay_capture(tmp_path, n_q, n_kv, H, Hk, kind):
     assert r["out"].shape == (n_q, H, D)
     bound = 2e-3 + 1e-2 * np.abs(r["ref"])    # north_star tolerance: max-abs 2e-3, rel 1e-2
     assert (np.abs(r["out"] - r["ref"]) <= bound).all(), (r["max_abs"], r["dispatch"])
+
+
+@pytest.mark.parametrize("n_q,n_kv,H,Hk", [(1, 256, 32, 8), (5, 320, 8, 8)])
+def test_replay_capture_in_the_cache_view_layout(tmp_path, n_q, n_kv, H, Hk):
+    """The reference's live GPU arm reads the same files as [n_kv][head][D] for both K and V (flash-matrix.cu:141,149): the layout is
+    derived from the shapes stored in the file headers, and an explicit layout that does not fit the files is an error."""
+    P = pkg()
+    D = 128
+    Q, K, V = synth_qkv(D, n_q, n_kv, H, Hk)
+    Q, K, V = Q[0], K[0], V[0]
+    mask = make_mask("noise", n_q, n_kv)
+    exp = _expected(Q, K, np.ascontiguousarray(V.transpose(0, 2, 1)), mask, 1.0 / np.sqrt(D))
+    paths = P.capture_paths(str(tmp_path), "cv")
+    Kc, Vc = np.ascontiguousarray(K.transpose(1, 0, 2)), np.ascontiguousarray(V.transpose(1, 0, 2))   # [n_kv][head][D]
+    for part, arr in zip(P.tensor_io.CAPTURE_PARTS, (Q, Kc, Vc, mask, exp)):
+        P.write_tensor(paths[part], f"fa-{part}", arr)
+    r = P.replay_capture(str(tmp_path), "cv")
+    assert r["kv_layout"] == "cache_view"
+    assert (np.abs(r["out"] - r["ref"]) <= 2e-3 + 1e-2 * np.abs(r["ref"])).all(), r["max_abs"]
+    r2 = P.replay_capture(str(tmp_path), "cv", kv_layout="cache_view")
+    assert np.array_equal(r2["out"], r["out"])
+
+
+def test_replay_capture_rejects_shapes_that_fit_no_layout(tmp_path):
+    P = pkg()
+    D, n_q, n_kv, H = 128, 1, 256, 4
+    Q, K, V = synth_qkv(D, n_q, n_kv, H, H)
+    paths = P.capture_paths(str(tmp_path), "bad")
+    bad_k = np.zeros((H, n_kv // 2, D), np.float16)  # half the keys the mask announces
+    for part, arr in zip(P.tensor_io.CAPTURE_PARTS, (Q[0], bad_k, bad_k, make_mask("zeros", n_q, n_kv), np.zeros((n_q, H, D), np.float32))):
+        P.write_tensor(paths[part], f"fa-{part}", arr)
+    with pytest.raises(P.B200FAError):
+        P.replay_capture(str(tmp_path), "bad")
