@@ -91,7 +91,7 @@ struct Shape {
 Shape make_shape(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03, int64_t ne11, int64_t ne12, int64_t ne13,
                  int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23, const void* k, const void* v,
                  int64_t kv_pos0, int64_t n_kv_total) {
-    return Shape{q_type, kv_type, ne00 <= 64 ? 64 : 128, ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
+    return Shape{q_type, kv_type, ne00 <= 64 ? 64 : (ne00 <= 128 ? 128 : 256), ne01, ne02, ne03, ne11, ne12, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total, ne00, ne13};
 }
 
 bool stream_eligible(const Shape& sh, bool sizing) {
@@ -259,10 +259,11 @@ int validate(const void* q, const void* k, const void* v, const void* out, int q
     if (q_type != B200FA_TYPE_F32 && q_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
     if (kv_type != B200FA_TYPE_F16 && kv_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
     if (dst_type != B200FA_TYPE_F32 && dst_type != B200FA_TYPE_F16) return B200FA_ERR_UNSUPPORTED;
-    // f16 K/V: any head size that is a multiple of 8 up to 128 (80, 96, 112 ... run zero-padded on the 64/128 kernels);
-    // q8_0 K/V and the partial (sequence-split) entries: 64 or 128 only
-    if (ne00 % 8 || ne00 > 128) return B200FA_ERR_UNSUPPORTED;
-    if ((kv_type == B200FA_TYPE_Q8_0 || out_is_partial) && ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
+    // f16 K/V: any head size that is a multiple of 8 up to 256 (80, 96, 112, 160, 192 ... run zero-padded on the 64 / 128 / 256 wide
+    // kernels); q8_0 K/V: 64, 128 or 256; the partial (sequence-split) entries: 64 or 128 only
+    if (ne00 % 8 || ne00 > 256) return B200FA_ERR_UNSUPPORTED;
+    if (kv_type == B200FA_TYPE_Q8_0 && ne00 != 64 && ne00 != 128 && ne00 != 256) return B200FA_ERR_UNSUPPORTED;
+    if (out_is_partial && ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
     if (ne11 > 0x7fffffff || ne01 > 0x7fffffff || ne02 > 65535 || ne03 * ne12 > 65535) return B200FA_ERR_UNSUPPORTED;
     const int64_t qrow = ne00 * (q_type == B200FA_TYPE_F32 ? 4 : 2);
     if (nb01 < qrow || ((uintptr_t)q | nb01 | nb02 | nb03) % 16) return B200FA_ERR_INVALID;
@@ -314,7 +315,8 @@ int run_rows16(FaParams& p, const Plan& pl, cudaStream_t st) {
     int rc;
     const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
 #define B200FA_ROWS16(DD, RR) (ext ? launch_rows16<DD, RR, true>(p, pl.n_groups, st) : launch_rows16<DD, RR, false>(p, pl.n_groups, st))
-    if (p.D == 128) rc = small ? B200FA_ROWS16(128, 1) : B200FA_ROWS16(128, 2);
+    if (p.D == 256) rc = small ? B200FA_ROWS16(256, 1) : B200FA_ROWS16(256, 2);  // head sizes 129..256: this kernel only
+    else if (p.D == 128) rc = small ? B200FA_ROWS16(128, 1) : B200FA_ROWS16(128, 2);
     else rc = small ? B200FA_ROWS16(64, 1) : B200FA_ROWS16(64, 2);
 #undef B200FA_ROWS16
     g_last_launches++;
@@ -475,8 +477,8 @@ size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01
     const DeviceInfo& di = device_info();
     const int sms = di.ok ? di.sm_count : 148;
     if (ne12 <= 0 || ne02 % ne12 || ne00 <= 0 || ne01 <= 0 || ne03 <= 0 || ne11 <= 0) return 0;
-    if (ne00 > 128) return 0;
-    Shape sh{q_type, kv_type, ne00 <= 64 ? 64 : 128, ne01, ne02, ne03, ne11, ne12, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11, ne00, ne13 > 0 ? ne13 : ne03};
+    if (ne00 > 256) return 0;
+    Shape sh = make_shape(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13 > 0 ? ne13 : ne03, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11);
     size_t m = 0;
     for (int variant = 0; variant < 5; variant++) {  // every path the two entry points can take for this shape
         const bool partial = variant == 1 || variant == 3;
@@ -514,7 +516,7 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     if (!di.ok || di.cc_major != 10) return B200FA_ERR_CUDA;  // sm_100a only, no fallback
 
     if (!(scale > 0.f)) flags |= B200FA_FLAG_NO_TCGEN05;  // the tile kernel takes row maxima of raw scores
-    const int64_t Dp = ne00 <= 64 ? 64 : 128;  // structural head size of the decode kernels; the prefill kernel is always 128 wide
+    const int64_t Dp = ne00 <= 64 ? 64 : (ne00 <= 128 ? 128 : 256);  // structural head size of the decode kernels; the prefill kernel is always 128 wide
     const float max_bias = ext ? ext->max_bias : 0.f, softcap = ext ? ext->logit_softcap : 0.f;
     if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
     Shape sh = make_shape(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total);
@@ -633,10 +635,10 @@ int b200fa_plan(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne0
                 int64_t ne13, uint32_t flags, int sm_count, b200fa_plan_info* out) {
     if (!out || sm_count < 1) return B200FA_ERR_INVALID;
     if (ne00 <= 0 || ne01 <= 0 || ne02 <= 0 || ne03 <= 0 || ne11 <= 0 || ne12 <= 0 || ne13 <= 0 || ne02 % ne12 || ne03 % ne13) return B200FA_ERR_INVALID;
-    if (ne00 % 8 || ne00 > 128) return B200FA_ERR_UNSUPPORTED;
-    if (kv_type == B200FA_TYPE_Q8_0 && ne00 != 64 && ne00 != 128) return B200FA_ERR_UNSUPPORTED;
+    if (ne00 % 8 || ne00 > 256) return B200FA_ERR_UNSUPPORTED;
+    if (kv_type == B200FA_TYPE_Q8_0 && ne00 != 64 && ne00 != 128 && ne00 != 256) return B200FA_ERR_UNSUPPORTED;
     if (kv_type != B200FA_TYPE_F16 && kv_type != B200FA_TYPE_Q8_0) return B200FA_ERR_UNSUPPORTED;
-    const int64_t Dp = ne00 <= 64 ? 64 : 128;
+    const int64_t Dp = ne00 <= 64 ? 64 : (ne00 <= 128 ? 128 : 256);
     const int64_t row = kv_type == B200FA_TYPE_Q8_0 ? Dp / kQ8BlockElems * kQ8BlockBytes : ne00 * 2;
     Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, row, row * ne11, row * ne11 * ne12, row, row * ne11, row * ne11 * ne12,
              (const void*)256, (const void*)256, 0, ne11, ne00, ne13};

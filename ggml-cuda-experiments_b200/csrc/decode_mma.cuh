@@ -126,7 +126,7 @@ struct KVTile {
 template <int D, int KV_TYPE, int RH, bool FIFO = true, bool EXT = false>
 __global__ void __launch_bounds__(kDecodeWarps * 32, 2)
 fa_rows16_splitkv(const __grid_constant__ FaParams p) {
-    static_assert(D == 64 || D == 128, "head size");
+    static_assert(D == 64 || D == 128 || D == 256, "head size");
     constexpr int NC4 = D / 32;   // 16-byte chunks per lane per K row (c loop) == q8_0 blocks per row
     constexpr int NCV = D / 64;   // 64-wide halves of a V row
     constexpr int NT = D / 8;     // output n-tiles

@@ -79,9 +79,16 @@ def test_plan_matches_workspace_size():
         assert p.workspace_size(*args) >= pl.workspace_bytes, args
 
 
+def test_head_sizes_above_128_plan_the_16_row_kernel():
+    p = P()
+    for D, n_q in [(256, 1), (192, 1), (256, 300), (160, 20)]:
+        assert plan(F32, F16, D, n_q, 32, 1, 4096, 8).kind == p.PLAN_ROWS16
+    assert plan(F32, Q8, 256, 1, 32, 1, 4096, 8).kind == p.PLAN_ROWS16
+
+
 def test_plan_rejects_bad_shapes():
     p = P()
-    for bad in [dict(D=100), dict(D=256), dict(H=30), dict(n_kv=0), dict(kv=Q8, D=96)]:
+    for bad in [dict(D=100), dict(D=264), dict(H=30), dict(n_kv=0), dict(kv=Q8, D=96)]:
         a = dict(q=F32, kv=F16, D=128, n_q=1, H=32, B=1, n_kv=256, Hk=8)
         a.update(bad)
         with pytest.raises(p.B200FAError):
