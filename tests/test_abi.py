@@ -70,9 +70,9 @@ def test_argument_validation_needs_no_gpu():
     assert call(q=None) == -1                 # NULL pointer
     assert call(H=30) == -1                   # heads not a multiple of kv heads
     assert call(nb11=250) == -1               # misaligned rows
-    assert call(D=256) == -2                  # head size not built
+    assert call(D=264, nb11=528) == -2        # head size not built (above 256)
     assert call(D=100) == -2                  # head size not a multiple of 8
-    assert call(D=96, kt=8, nb11=102) == -2   # q8_0 K/V: 64 or 128 only
+    assert call(D=96, kt=8, nb11=102) == -2   # q8_0 K/V: 64, 128 or 256 only
     assert call(kt=2) == -2                   # type not built (q4_0)
     assert call(k=(1 << 21) + 2) == -1        # misaligned base
 
