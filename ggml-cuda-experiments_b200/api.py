@@ -157,7 +157,8 @@ class Workspace:
 
 class ExtParams(C.Structure):
     """b200fa_ext_params: the upstream-ggml score modifiers of b200fa_flash_attn_ext2."""
-    _fields_ = [("max_bias", C.c_float), ("logit_softcap", C.c_float)]
+    _fields_ = [("max_bias", C.c_float), ("logit_softcap", C.c_float),
+                ("mask_ne2", C.c_int64), ("mask_ne3", C.c_int64), ("mask_nb2", C.c_int64), ("mask_nb3", C.c_int64)]
 
 
 class PlanInfo(C.Structure):
@@ -182,10 +183,11 @@ def plan(q_type, kv_type, D, n_q, n_head, n_batch, n_kv, n_head_kv, n_batch_kv=N
 
 
 def flash_attn_ext_raw(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb,
-                       flags, ws_ptr, ws_bytes, stream_ptr, max_bias: float = 0.0, logit_softcap: float = 0.0) -> int:
-    """The ABI call.  q,k,v,mask,dst are device addresses (ints); returns the status code."""
-    if max_bias != 0.0 or logit_softcap != 0.0:
-        ext = ExtParams(max_bias, logit_softcap)
+                       flags, ws_ptr, ws_bytes, stream_ptr, max_bias: float = 0.0, logit_softcap: float = 0.0, mask_slices=None) -> int:
+    """The ABI call.  q,k,v,mask,dst are device addresses (ints); returns the status code.
+    mask_slices = (ne32, ne33, nb32, nb33): one mask per head / per batch entry (b200fa_ext_params)."""
+    if max_bias != 0.0 or logit_softcap != 0.0 or mask_slices is not None:
+        ext = ExtParams(max_bias, logit_softcap, *(mask_slices or (0, 0, 0, 0)))
         return lib().b200fa_flash_attn_ext2(
             q, k, v, mask, dst, scale, q_type, kv_type, dst_type, *q_ne, *k_ne, ne31, nb31,
             q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3],
@@ -203,7 +205,9 @@ def flash_attn_ext(q, k, v, mask=None, scale=None, dst=None, dst_dtype=None, fla
 
     q  : [n_batch][n_head][n_q][D] view (any strides with 16-byte aligned rows), f32 or f16
     k,v: [n_batch_kv][n_head_kv][n_kv][D] f16 views, or uint8 [..][n_kv][D/32*34] for q8_0
-    mask: f16 [>= n_q][n_kv] or None.  Returns dst (allocated if not given).
+    mask: f16 [>= n_q][n_kv] or None — or 4-D [ne33][ne32][>= n_q][n_kv] with ne32 in {1, n_head}, ne33 in {1, n_batch}: one mask
+          slice per head and / or per batch entry (upstream ggml's broadcast; goes through b200fa_flash_attn_ext2).
+    Returns dst (allocated if not given).
     """
     import torch
     if not q.is_cuda:
@@ -216,21 +220,31 @@ def flash_attn_ext(q, k, v, mask=None, scale=None, dst=None, dst_dtype=None, fla
     if dst is None:
         dst = torch.empty((n_b, n_q, n_head, D), dtype=dst_dtype or torch.float32, device=q.device)
     dt = _type_of(dst)
+    slices = None
+    if mask is not None and mask.dim() == 4:
+        slices = (mask.shape[1], mask.shape[0], mask.stride(1) * 2, mask.stride(0) * 2)
+        m_ptr, ne31, nb31 = mask.data_ptr(), mask.shape[2], mask.stride(2) * 2
+    else:
+        m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
     if workspace is None:
-        workspace = _temp_workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device, stream)
-    m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
+        ext = ExtParams(max_bias, logit_softcap, *(slices or (0, 0, 0, 0)))
+        l = lib()
+        l.b200fa_workspace_size_ext2.restype = C.c_size_t
+        l.b200fa_workspace_size_ext2.argtypes = [C.c_int, C.c_int] + [C.c_int64] * 7 + [C.c_void_p, C.c_uint32]
+        workspace = _temp_workspace(l.b200fa_workspace_size_ext2(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], C.byref(ext), flags), q.device, stream)
     with _on_device_of(q):
         rc = flash_attn_ext_raw(q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, dst.data_ptr(), scale, qt, kt, dt,
                             q_ne, k_ne, ne31, nb31, q_nb, k_nb, v_nb, flags, workspace.ptr, workspace.nbytes,
-                            _stream_ptr(stream), max_bias, logit_softcap)
+                            _stream_ptr(stream), max_bias, logit_softcap, slices)
     if rc != 0:
         raise B200FAError(rc, "b200fa_flash_attn_ext")
     return dst
 
 
 def flash_attn_partial(q, k, v, mask=None, scale=None, kv_pos0=0, n_kv_total=None, flags=0,
-                       workspace: Workspace | None = None, stream=None, kv_type=None, out=None):
-    """Sequence-split building block: per-row (O~[D], m, l) over this device's KV slice -> f32 [rows][D+2]."""
+                       workspace: Workspace | None = None, stream=None, kv_type=None, out=None, max_bias: float = 0.0, logit_softcap: float = 0.0):
+    """Sequence-split building block: per-row (O~[D], m, l) over this device's KV slice -> f32 [rows][D+2].
+    max_bias / logit_softcap: the score modifiers of flash_attn_ext (b200fa_flash_attn_partial2); `mask` holds this slice's columns."""
     import torch
     qt, kt = _type_of(q), _type_of(k, kv_type)
     q_ne, q_nb = _ne_nb(q, qt); k_ne, k_nb = _ne_nb(k, kt); _, v_nb = _ne_nb(v, kt)
@@ -244,11 +258,15 @@ def flash_attn_partial(q, k, v, mask=None, scale=None, kv_pos0=0, n_kv_total=Non
     if workspace is None:
         workspace = _temp_workspace(workspace_size(qt, kt, *q_ne, k_ne[1], k_ne[2], k_ne[3], flags), q.device, stream)
     m_ptr, ne31, nb31 = (mask.data_ptr(), mask.shape[0], mask.stride(0) * 2) if mask is not None else (None, 0, 0)
+    ext = ExtParams(max_bias, logit_softcap, 0, 0, 0, 0)
+    l = lib()
+    l.b200fa_flash_attn_partial2.restype = C.c_int
+    l.b200fa_flash_attn_partial2.argtypes = [C.c_void_p] * 5 + [C.c_float] + [C.c_int] * 2 + [C.c_int64] * 21 + [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
     with _on_device_of(q):
-        rc = lib().b200fa_flash_attn_partial(
+        rc = l.b200fa_flash_attn_partial2(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), m_ptr, out.data_ptr(), scale, qt, kt, *q_ne, *k_ne, ne31, nb31,
         q_nb[1], q_nb[2], q_nb[3], k_nb[1], k_nb[2], k_nb[3], v_nb[1], v_nb[2], v_nb[3], kv_pos0, n_kv_total,
-        flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
+        C.byref(ext) if (max_bias != 0.0 or logit_softcap != 0.0) else None, flags, workspace.ptr, workspace.nbytes, _stream_ptr(stream))
     if rc != 0:
         raise B200FAError(rc, "b200fa_flash_attn_partial")
     return out

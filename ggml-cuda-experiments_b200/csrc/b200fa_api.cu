@@ -83,7 +83,8 @@ struct Shape {
     int64_t kv_pos0, n_kv_total;
     int64_t Dr = 0;  // real head size when it differs from the structural D (0 = same)
     int64_t n_batch_kv = 0;  // ne13 (0 = n_batch)
-    bool ext = false;  // ALiBi / soft-cap requested (ext2 entry): only the persistent prefill kernel implements them
+    bool ext = false;  // ALiBi / soft-cap / mask slices requested (ext2 entry): only the persistent prefill kernel implements them
+    int64_t mask_slices = 1;  // m_ne2 * m_ne3 (ext2): the prefill kernel keeps one table of mask tile classes per slice
 };
 
 // The one place a call's arguments become the planner's view of it (attn_common, b200fa_flash_attn_seqpar and b200fa_plan agree by
@@ -137,7 +138,7 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
         pl.kind = kPrefill;
         if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * 128 * 2), 256);
         const int64_t qt = (n_q + 127) / 128, kt = (n_kv + 127) / 128;
-        pl.cls_bytes = align_up((size_t)(qt * kt), 256);
+        pl.cls_bytes = align_up((size_t)(qt * kt * sh.mask_slices), 256);
         pl.ctr_bytes = kCtrRegion;
         // Split-KV prefill: fewer work items than SMs and a long KV range (chunked prefill, long-context continuation): cut every
         // item's KV tiles into n_splits segments, each its own work item emitting (O~, m, l) rows, merged by a second launch.
@@ -313,7 +314,7 @@ int launch_rows16(const FaParams& p, int n_groups, cudaStream_t st) {
 int run_rows16(FaParams& p, const Plan& pl, cudaStream_t st) {
     const bool small = (int64_t)p.n_q * p.gqa <= 8;  // one group of at most 8 rows: only fragment rows g are live
     int rc;
-    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0 || p.m_ne2 * p.m_ne3 > 1;
 #define B200FA_ROWS16(DD, RR) (ext ? launch_rows16<DD, RR, true>(p, pl.n_groups, st) : launch_rows16<DD, RR, false>(p, pl.n_groups, st))
     if (p.D == 256) rc = small ? B200FA_ROWS16(256, 1) : B200FA_ROWS16(256, 2);  // head sizes 129..256: this kernel only
     else if (p.D == 128) rc = small ? B200FA_ROWS16(128, 1) : B200FA_ROWS16(128, 2);
@@ -395,7 +396,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     { static const bool nd = tune_env("B200FA_NO_DEEP_RING") != nullptr; if (nd) a.deep_ring = 0; }
     { static const int rg = tune_env("B200FA_RING") ? atoi(tune_env("B200FA_RING")) : 0; a.ring = rg; }
     a.peers = g_seqpar.peers; a.rank = g_seqpar.rank; a.world = g_seqpar.world; a.fdst = g_seqpar.fdst; a.fdst_type = g_seqpar.fdst_type;
-    a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31) % 16) == 0) ? 1 : 0;
+    a.mask_bulk = (p.mask != nullptr && ((((uintptr_t)p.mask) | (uintptr_t)p.nb31 | (uintptr_t)p.nb32 | (uintptr_t)p.nb33) % 16) == 0) ? 1 : 0;
     { static const bool nb = tune_env("B200FA_NO_MASK_BULK") != nullptr; if (nb) a.mask_bulk = 0; }
     CUtensorMap tk{}, tv{};
     if (p.kv_type == B200FA_TYPE_F16) {
@@ -417,7 +418,7 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     static const int force_rh = tune_env("B200FA_STREAM_RH") ? atoi(tune_env("B200FA_STREAM_RH")) : 0;  // tuning: 2 = always the 16-row variant
     const bool small = (int64_t)p.n_q * p.gqa <= 8 && force_rh != 2;
     g_last_launches++;
-    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0 || p.m_ne2 * p.m_ne3 > 1;
 #define B200FA_STREAM_E(DD, KK, EE) (small ? launch_stream_t<DD, KK, 1, EE>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2, EE>(p, a, pl.grid, tk, tv, st))
 #define B200FA_STREAM(DD, KK) (ext ? B200FA_STREAM_E(DD, KK, true) : B200FA_STREAM_E(DD, KK, false))
 #define B200FA_STREAM_T8(DD) (ext ? launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, true, true>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, false, true>(p, a, pl.grid, tk, tv, st))
@@ -474,11 +475,20 @@ int b200fa_last_launch_count(void) { return g_last_launches; }
 
 size_t b200fa_workspace_size(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
                              int64_t ne11, int64_t ne12, int64_t ne13, uint32_t flags) {
+    return b200fa_workspace_size_ext2(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, nullptr, flags);
+}
+
+size_t b200fa_workspace_size_ext2(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                                  int64_t ne11, int64_t ne12, int64_t ne13, const b200fa_ext_params* ext, uint32_t flags) {
     const DeviceInfo& di = device_info();
     const int sms = di.ok ? di.sm_count : 148;
     if (ne12 <= 0 || ne02 % ne12 || ne00 <= 0 || ne01 <= 0 || ne03 <= 0 || ne11 <= 0) return 0;
     if (ne00 > 256) return 0;
     Shape sh = make_shape(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13 > 0 ? ne13 : ne03, 0, 0, 0, 0, 0, 0, nullptr, nullptr, 0, ne11);
+    if (ext) {  // mask slices: one table of mask tile classes per slice on the prefill path
+        sh.mask_slices = (ext->mask_ne2 > 0 ? ext->mask_ne2 : 1) * (ext->mask_ne3 > 0 ? ext->mask_ne3 : 1);
+        sh.ext = ext->max_bias > 0.f || ext->logit_softcap != 0.f || sh.mask_slices > 1;
+    }
     size_t m = 0;
     for (int variant = 0; variant < 5; variant++) {  // every path the two entry points can take for this shape
         const bool partial = variant == 1 || variant == 3;
@@ -519,8 +529,16 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     const int64_t Dp = ne00 <= 64 ? 64 : (ne00 <= 128 ? 128 : 256);  // structural head size of the decode kernels; the prefill kernel is always 128 wide
     const float max_bias = ext ? ext->max_bias : 0.f, softcap = ext ? ext->logit_softcap : 0.f;
     if (!(max_bias >= 0.f) || !(softcap == softcap) || isinf(softcap) || isinf(max_bias)) return B200FA_ERR_INVALID;
+    // mask slices (upstream ggml's ne32 / ne33 broadcast): one mask per head and / or per batch entry instead of the reference's shared one
+    const int64_t m_ne2 = ext && ext->mask_ne2 > 0 ? ext->mask_ne2 : 1, m_ne3 = ext && ext->mask_ne3 > 0 ? ext->mask_ne3 : 1;
+    if (m_ne2 * m_ne3 > 1) {
+        if (!mask || (m_ne2 != 1 && m_ne2 != ne02) || (m_ne3 != 1 && m_ne3 != ne03)) return B200FA_ERR_INVALID;
+        if ((m_ne2 > 1 && (ext->mask_nb2 < ne31 * nb31 || ext->mask_nb2 % 2)) || (m_ne3 > 1 && (ext->mask_nb3 <= 0 || ext->mask_nb3 % 2))) return B200FA_ERR_INVALID;
+        if (want_partial) return B200FA_ERR_UNSUPPORTED;  // the sequence-split entries take the shared mask only
+    }
     Shape sh = make_shape(q_type, kv_type, ne00, ne01, ne02, ne03, ne11, ne12, ne13, nb11, nb12, nb13, nb21, nb22, nb23, k, v, kv_pos0, n_kv_total);
-    sh.ext = max_bias > 0.f || softcap != 0.f;
+    sh.ext = max_bias > 0.f || softcap != 0.f || m_ne2 * m_ne3 > 1;
+    sh.mask_slices = m_ne2 * m_ne3;
     // 17..128 rows per KV head from a GQA group (a burst of up to 16 query positions, e.g. speculative decoding): split every real
     // KV head into kv_div VIRTUAL heads of gqa / kv_div q heads each, so that a unit has <= 16 rows and the stream kernel applies.
     // K/V are streamed kv_div times, but by CTAs working side by side: the repeats are L2 hits (8 positions x GQA 4, batch 8,
@@ -548,6 +566,8 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     p.nb11 = nb11; p.nb12 = nb12; p.nb13 = nb13;
     p.nb21 = nb21; p.nb22 = nb22; p.nb23 = nb23;
     p.nb31 = nb31;
+    p.m_ne2 = (int)m_ne2; p.m_ne3 = (int)m_ne3;
+    p.nb32 = m_ne2 > 1 ? ext->mask_nb2 : 0; p.nb33 = m_ne3 > 1 ? ext->mask_nb3 : 0;
     p.causal = (flags & B200FA_FLAG_CAUSAL) ? 1 : 0;
     p.kv_pos0 = kv_pos0;
     p.causal_off = n_kv_total - ne01;
@@ -682,10 +702,23 @@ int b200fa_flash_attn_partial(const void* q, const void* k, const void* v, const
                               int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
                               int64_t kv_pos0, int64_t n_kv_total,
                               uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
+    return b200fa_flash_attn_partial2(q, k, v, mask, partial, scale, q_type, kv_type, ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13, ne31, nb31,
+                                      nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0, n_kv_total, nullptr, flags, workspace,
+                                      workspace_bytes, stream);
+}
+
+int b200fa_flash_attn_partial2(const void* q, const void* k, const void* v, const void* mask, float* partial, float scale,
+                               int q_type, int kv_type,
+                               int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+                               int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+                               int64_t ne31, int64_t nb31, int64_t nb01, int64_t nb02, int64_t nb03,
+                               int64_t nb11, int64_t nb12, int64_t nb13, int64_t nb21, int64_t nb22, int64_t nb23,
+                               int64_t kv_pos0, int64_t n_kv_total, const b200fa_ext_params* ext,
+                               uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream) {
     if (!partial || kv_pos0 < 0 || n_kv_total < kv_pos0 + ne11) return B200FA_ERR_INVALID;
     return attn_common(q, k, v, mask, nullptr, partial, scale, q_type, kv_type, B200FA_TYPE_F32, ne00, ne01, ne02, ne03,
                        ne10, ne11, ne12, ne13, ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, kv_pos0,
-                       n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+                       n_kv_total, flags, workspace, workspace_bytes, (cudaStream_t)stream, ext);
 }
 
 size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D) {

@@ -49,6 +49,11 @@ struct FaParams {
     int64_t nb11, nb12, nb13;
     int64_t nb21, nb22, nb23;
     int64_t nb31;
+    // mask slices (b200fa_flash_attn_ext2, upstream ggml's ne32/ne33 broadcast): m_ne2 in {1, n_head}, m_ne3 in {1, n_batch}; the mask row
+    // of (query iq1, head iq2, batch iq3) starts at mask + iq1*nb31 + (iq2 % m_ne2)*nb32 + (iq3 % m_ne3)*nb33.  The reference shares one
+    // mask between heads and batches (flash-llama.h:151,194): m_ne2 = m_ne3 = 1.
+    int m_ne2, m_ne3;
+    int64_t nb32, nb33;
     int causal;          // B200FA_FLAG_CAUSAL
     int64_t kv_pos0;     // global position of this slice's first key (sequence-split); 0 otherwise
     int64_t causal_off;  // a query at iq1 sees global kv positions <= iq1 + causal_off  (n_kv_total - n_q)
@@ -63,6 +68,15 @@ struct FaParams {
     float cap_out;               //                 cap * log2(e)
     float cap_raw;               // cap / scale: tanh(qk * cap_in) * cap_raw is the capped score in RAW (unscaled) units
 };
+
+// byte offset of the mask slice of (head iq2, batch iq3)
+__device__ __forceinline__ int64_t fa_mask_slice_off(const FaParams& p, int iq2, int iq3) {
+    return (p.m_ne2 > 1 ? (int64_t)iq2 * p.nb32 : 0) + (p.m_ne3 > 1 ? (int64_t)iq3 * p.nb33 : 0);
+}
+// index of that slice in per-slice tables (mask tile classes of the prefill kernel)
+__device__ __forceinline__ int fa_mask_slice(const FaParams& p, int iq2, int iq3) {
+    return (p.m_ne2 > 1 ? iq2 : 0) + p.m_ne2 * (p.m_ne3 > 1 ? iq3 : 0);
+}
 
 // ALiBi slope of query head h (1 when off)
 __device__ __forceinline__ float fa_slope(const FaParams& p, int h) {

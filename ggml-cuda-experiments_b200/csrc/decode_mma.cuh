@@ -198,10 +198,10 @@ fa_rows16_splitkv(const __grid_constant__ FaParams p) {
     const char* vbase = p.v + (int64_t)ik2 * p.nb22 + (int64_t)ik3 * p.nb23;
     const char* mrow[RH];
 #pragma unroll
-    for (int h = 0; h < RH; h++) mrow[h] = p.mask ? p.mask + iq1r[h] * p.nb31 : nullptr;
+    for (int h = 0; h < RH; h++) mrow[h] = p.mask ? p.mask + iq1r[h] * p.nb31 + (EXT ? fa_mask_slice_off(p, iq2r[h], iq3) : 0) : nullptr;
     const bool al8 = Q8 && ((((uintptr_t)p.k | (uintptr_t)p.v | (uintptr_t)p.nb11 | (uintptr_t)p.nb12 | (uintptr_t)p.nb13 |
                               (uintptr_t)p.nb21 | (uintptr_t)p.nb22 | (uintptr_t)p.nb23) & 7) == 0);
-    const bool mask_al8 = p.mask != nullptr && ((((uintptr_t)p.mask | (uintptr_t)p.nb31) & 7) == 0);
+    const bool mask_al8 = p.mask != nullptr && ((((uintptr_t)p.mask | (uintptr_t)p.nb31 | (uintptr_t)p.nb32 | (uintptr_t)p.nb33) & 7) == 0);
     const int last = p.n_kv - 1;
     // Per-lane running row pointers: a full tile costs one 64-bit add per stream, no multiplies.
     constexpr int kStrideKV = kDecodeWarps * kTileKV;

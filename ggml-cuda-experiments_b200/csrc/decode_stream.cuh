@@ -279,15 +279,23 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         // only when the run crosses into the next unit.
         int pu = (int)((start + pfirst) / (unsigned)a.cph), pch = (int)(start + pfirst - (unsigned)pu * (unsigned)a.cph);  // unit / chunk of the next issue
         int ik2 = 0, ik3 = 0;  // the REAL kv head / kv batch whose K/V the (possibly virtual) unit pu streams
+        int m_head0 = 0;       // EXT, per-head masks: first q head of the unit (its rows' heads are m_head0 + R % gqa)
+        int64_t m_unit_off = 0;  // EXT, per-batch masks: byte offset of the unit's batch slice
         auto set_unit = [&](int u) {
             const int iq3 = u / p.n_head_kv;
             ik3 = iq3 / p.rk3;
             ik2 = (u - iq3 * p.n_head_kv) / p.kv_div;
+            if constexpr (EXT) {
+                m_head0 = (u - iq3 * p.n_head_kv) * p.gqa;
+                m_unit_off = p.m_ne3 > 1 ? (int64_t)iq3 * p.nb33 : 0;
+            }
         };
         set_unit(pu);
         const int q8_box_chunks = (Q8 && a.q8_lines > 0) ? (int)(((int64_t)a.q8_lines * 128) / Geo::kKBytes) : 0;  // chunks of a head inside the line maps
         const int whole_chunks = p.n_kv / DK_CHUNK;                                        // chunks with all 64 keys
-        const int mrows_full = ((Q8 ? !isV : which == DK_PWARPS - 1) && a.mask_bulk) ? p.n_q : 0;
+        // one staged 128-byte mask line per query position — or, with per-head masks (EXT, m_ne2 > 1), per row of the unit
+        const bool m_per_row = EXT && p.m_ne2 > 1;
+        const int mrows_full = ((Q8 ? !isV : which == DK_PWARPS - 1) && a.mask_bulk) ? (m_per_row ? p.n_q * p.gqa : p.n_q) : 0;
         const CUtensorMap* tm = isV ? &tmV : &tmK;
         const bool has_box = box < Geo::kBoxes;                  // (D = 64, f16: one box per tensor)
         const uint32_t half_off = isV ? Geo::kVOff : 0;          // this producer's half of a stage
@@ -322,8 +330,17 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                 mbar_arrive_expect_tx(&full[stage], nb16 + mrows * 128);
                 if (nb16 > 0) bulk_g2s(sb, src, nb16, &full[stage]);
             }
-            for (int r = 0; r < mrows; r++)
-                bulk_g2s(stages_u32 + stage * Geo::kStageBytes + Geo::kMaskOff + r * 128, p.mask + (int64_t)r * p.nb31 + (int64_t)key0 * 2, 128, &full[stage]);
+            if (!m_per_row) {
+                for (int r = 0; r < mrows; r++)
+                    bulk_g2s(stages_u32 + stage * Geo::kStageBytes + Geo::kMaskOff + r * 128, p.mask + (EXT ? m_unit_off : 0) + (int64_t)r * p.nb31 + (int64_t)key0 * 2, 128, &full[stage]);
+            } else {  // line R = row R of the unit: query position R / gqa, head m_head0 + R % gqa
+                int iq1 = 0, hq = 0;
+                for (int r = 0; r < mrows; r++) {
+                    bulk_g2s(stages_u32 + stage * Geo::kStageBytes + Geo::kMaskOff + r * 128,
+                             p.mask + m_unit_off + (int64_t)iq1 * p.nb31 + (int64_t)(m_head0 + hq) * p.nb32 + (int64_t)key0 * 2, 128, &full[stage]);
+                    if (++hq == p.gqa) { hq = 0; iq1++; }
+                }
+            }
             pch += PSTRIDE;
             if (pch >= a.cph) {
                 do { pch -= a.cph; pu++; } while (pch >= a.cph);
@@ -353,7 +370,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     const int g = lane >> 2, t = lane & 3;
     const int group = warp >> 2, sub = warp & 3;
     const int rows_total = p.n_q * p.gqa;
-    const bool mask_al8 = p.mask != nullptr && ((((uintptr_t)p.mask | (uintptr_t)p.nb31) & 7) == 0);
+    const bool mask_al8 = p.mask != nullptr && ((((uintptr_t)p.mask | (uintptr_t)p.nb31 | (uintptr_t)p.nb32 | (uintptr_t)p.nb33) & 7) == 0);
 
     // Full accumulator quads also when only fragment rows g are live (RH == 1): rows 8-15 of A are fed zeros, so entries 2-3 stay
     // what they were (zero) and the HMMA accumulates in place — no per-instruction re-zeroing or moves to build its C/D quad.
@@ -374,6 +391,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     bool rvalid[NR];
     int lim[NR];
     const char* mrow[NR];
+    int mline[NR];          // staged mask line of the row: its query position, or the row itself with per-head masks (EXT)
 #pragma unroll
     for (int h = 0; h < NR; h++) {
         const int R = T8 ? 2 * t + h : g + 8 * h;
@@ -383,6 +401,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const int64_t vis = p.causal ? (int64_t)iq1r[h] + p.causal_off - p.kv_pos0 + 1 : (int64_t)p.n_kv;
         lim[h] = (int)max((int64_t)0, min((int64_t)a.kv_end, vis));
         mrow[h] = p.mask ? p.mask + (int64_t)iq1r[h] * p.nb31 : nullptr;
+        mline[h] = (EXT && p.m_ne2 > 1) ? (rvalid[h] ? R : 0) : iq1r[h];
         mslope[h] = kLog2e;
     }
 
@@ -552,7 +571,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 #pragma unroll
             for (int h = 0; h < RH; h++) {
                 if (staged_mask) {
-                    T.mk[h] = lds64(sb + Geo::kMaskOff + iq1r[h] * 128 + (r0 + 4 * t) * 2);
+                    T.mk[h] = lds64(sb + Geo::kMaskOff + mline[h] * 128 + (r0 + 4 * t) * 2);
                 } else if (mask_al8 && kv0 + 16 <= p.n_kv) {
                     T.mk[h] = __ldg(reinterpret_cast<const uint2*>(mrow[h] + (int64_t)(kv0 + 4 * t) * 2));
                 } else {
@@ -683,7 +702,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
                 if (staged_mask) {
-                    const uint32_t ma = sb + Geo::kMaskOff + iq1r[rr] * 128 + (16 * sub + keyA) * 2;
+                    const uint32_t ma = sb + Geo::kMaskOff + mline[rr] * 128 + (16 * sub + keyA) * 2;
                     mkh[rr][0] = lds_u16(ma); mkh[rr][1] = lds_u16(ma + 4);
                 } else {
                     mkh[rr][0] = kvA < p.n_kv ? ld_u16(mrow[rr] + (int64_t)kvA * 2) : 0u;
@@ -849,6 +868,12 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const unsigned c0 = dk_owner((unsigned)u * a.cph, total, G), c1 = dk_owner((unsigned)(u + 1) * a.cph - 1u, total, G);
         const int n_contrib = (int)(c1 - c0 + 1);
 
+        if constexpr (EXT) {  // mask slices: the rows' mask pointers depend on the unit's heads and batch
+            if (p.mask != nullptr && (p.m_ne2 > 1 || p.m_ne3 > 1)) {
+#pragma unroll
+                for (int h = 0; h < NR; h++) mrow[h] = p.mask + (int64_t)iq1r[h] * p.nb31 + fa_mask_slice_off(p, ik2 * p.gqa + rq[h], iq3);
+            }
+        }
         // ---- Q fragments of this unit's rows (f16; an f32 Q is rounded like the reference does, flash-llama.h:80) ----
         if constexpr (T8) {
             // B fragments: lane (g, t) holds Q[row g][32b + 8t .. + 7]; then -1152 x the block sums of rows 2t, 2t+1

@@ -76,7 +76,8 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
         if (w >= 0) {
             decode_item(w, qt0, iq2, iq3);
             for (int j = lane; j < a.n_kv_tiles; j += 32) {
-                const int c = pf_tile_class(p, a, qt0, j, causal) | (pf_tile_class(p, a, qt0 + 1, j, causal) << 2);
+                const int ms = fa_mask_slice(p, iq2, iq3);
+                const int c = pf_tile_class(p, a, qt0, j, causal, ms) | (pf_tile_class(p, a, qt0 + 1, j, causal, ms) << 2);
                 sm.cls2[slot][j] = (uint8_t)c;
                 if (c != 0xA) { lo = min(lo, j); hi = max(hi, j + 1); }
             }
@@ -291,7 +292,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t tS = trow + PF_TM_S + 128u * t, tO = trow + PF_TM_O + 128u * t;
         const float c = p.scale_log2;
-        const bool mask_vec = (((uintptr_t)p.mask | (uintptr_t)p.nb31) & 15) == 0;
+        const bool mask_vec = (((uintptr_t)p.mask | (uintptr_t)p.nb31 | (uintptr_t)p.nb32 | (uintptr_t)p.nb33) & 15) == 0;
         const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
         int it_tot = 0;   // tiles done over all items (phase counter of s_full[t][h])
         int g_tot = 0;    // half tiles done over all items (phase counter of pv_done[t])
@@ -313,7 +314,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             const int qrow = q0 + r;
             // rows past n_q read the last real mask row (their results are never stored): every lane of a warp takes the
             // same path, so the .sync.aligned tcgen05 instructions below always see a converged warp
-            const char* mrow = (p.mask != nullptr && !causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 : nullptr;
+            const char* mrow = (p.mask != nullptr && !causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 + (EXT ? fa_mask_slice_off(p, iq2, iq3) : 0) : nullptr;
             const int64_t vis = causal ? (int64_t)qrow + p.causal_off : (int64_t)p.n_kv;  // last visible key (inclusive)
             float m_ref = -INFINITY, l = 0.f;
             const float mask_mul = EXT ? a.inv_scale * fa_slope(p, iq2) : a.inv_scale;  // mask values are folded into RAW scores: x slope / scale
@@ -573,7 +574,8 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {
         uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
-        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2);
+        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles, p.m_ne2 * p.m_ne3), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2,
+                                                                                              p.m_ne2, p.nb32, p.nb33);
         n++;
         a.cls = cls;
         pa.detect_causal = 1;
@@ -605,7 +607,7 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     constexpr size_t smem_bytes = sizeof(PpShared);
     static_assert(smem_bytes <= 227 * 1024, "prefill shared memory budget");
     static const int poly = tune_env("B200FA_POLY") ? atoi(tune_env("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
-    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0;  // ext2 score modifiers: their own instantiation
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0 || p.m_ne2 * p.m_ne3 > 1;  // ext2 score modifiers / mask slices: their own instantiation
 #ifdef B200FA_TUNING
     auto kern = ext ? fa_prefill_persistent<2, true>
                     : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));

@@ -69,9 +69,10 @@ struct PfArgs {
 };
 
 // 0 = every element visible, 1 = mixed (mask / causal edge / ragged tail), 2 = nothing visible.  qt = 128-row tile index.
-__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j, bool causal);
+// slice: index of the (head, batch) mask slice whose classes apply (fa_mask_slice; 0 for the reference's shared mask)
+__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j, bool causal, int slice = 0);
 __device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j) { return pf_tile_class(p, a, qt, j, p.causal != 0); }
-__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j, bool causal) {
+__device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a, int qt, int j, bool causal, int slice) {
     const int kv0 = j * PF_BN;
     if (kv0 >= p.n_kv || qt >= a.n_q_tiles) return 2;
     int c = (kv0 + PF_BN > p.n_kv) ? 1 : 0;
@@ -82,7 +83,7 @@ __device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a,
         if (kv0 > last_lim) return 2;
         if (kv0 + PF_BN - 1 > first_lim) c = 1;
     } else if (a.cls != nullptr) {
-        const int u = a.cls[(int64_t)qt * a.n_kv_tiles + j];
+        const int u = a.cls[((int64_t)slice * a.n_q_tiles + qt) * a.n_kv_tiles + j];
         if (u == 2) return 2;
         if (u == 1) c = 1;
     } else if (p.mask != nullptr) {
@@ -571,12 +572,16 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
 // *not_causal (may be null), the tiles that deviate from the exactly-causal pattern "0 where kv <= q + (n_kv - n_q), -inf
 // elsewhere": a caller that passes the usual causal mask tensor without B200FA_FLAG_CAUSAL still gets the synthesised
 // mask (no per-element mask reads in the attention kernel).
+// blockIdx.z = mask slice (head + m_ne2 * batch): its base is mask + (z % m_ne2) * nb32 + (z / m_ne2) * nb33, its classes follow those of slice z - 1
 __global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__ mask, int64_t nb31, int n_q, int n_kv,
-                                                        int n_kv_tiles, uint8_t* __restrict__ cls, unsigned int* not_causal) {
+                                                        int n_kv_tiles, uint8_t* __restrict__ cls, unsigned int* not_causal,
+                                                        int m_ne2 = 1, int64_t nb32 = 0, int64_t nb33 = 0) {
     const int j = blockIdx.x, qt = blockIdx.y;
+    mask += (int64_t)(blockIdx.z % m_ne2) * nb32 + (int64_t)(blockIdx.z / m_ne2) * nb33;
+    cls += (int64_t)blockIdx.z * gridDim.y * n_kv_tiles;
     const int off = n_kv - n_q;
     int has_zero = 0, has_ninf = 0, has_other = 0, deviates = 0;
-    const bool vec = ((((uintptr_t)mask | (uintptr_t)nb31) & 15) == 0) && (j + 1) * PF_BN <= n_kv;
+    const bool vec = ((((uintptr_t)mask | (uintptr_t)nb31) & 15) == 0) && (j + 1) * PF_BN <= n_kv;  // (mask already points at the slice)
     if (vec) {  // aligned, whole tile: 16-byte loads, 8 mask values each — all eight loads of a thread in flight at once (a rolled
                 // loop made this kernel eight dependent DRAM round trips long: 8 us for C3's 8 MB mask)
         constexpr int kIters = PF_BM * (PF_BN / 8) / 256;

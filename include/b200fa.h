@@ -18,7 +18,8 @@
  * Tensor description is ggml's: ne = element counts, nb = byte strides, fastest dimension first.
  *   q    : [ne00=D, ne01=n_q,  ne02=n_head,    ne03=n_batch]  f32 (reference) or f16
  *   k, v : [ne10=D, ne11=n_kv, ne12=n_head_kv, ne13=n_batch_kv] f16, or q8_0 (34-byte blocks of 32)
- *   mask : f16 [n_kv, ne31 >= n_q] rows = queries, row stride nb31 bytes, shared by heads/batches; may be NULL
+ *   mask : f16 [n_kv, ne31 >= n_q] rows = queries, row stride nb31 bytes, shared by heads/batches (per-head / per-sequence
+ *          slices: b200fa_flash_attn_ext2); may be NULL
  *   dst  : [D, n_head, n_q, n_batch] contiguous, f32 (reference) or f16
  *   GQA  : kv head = q head / (ne02/ne12); batch broadcast likewise (flash-llama.h:128-140).
  */
@@ -109,6 +110,12 @@ int b200fa_flash_attn_ext(
 typedef struct b200fa_ext_params {
     float max_bias;       /* >= 0; 0 = no ALiBi */
     float logit_softcap;  /* 0 = off */
+    /* Mask slices — upstream ggml's mask broadcast over heads (ne32) and batch entries (ne33); the reference shares ONE mask between
+     * all heads and batches (flash-llama.h:151,194), which is mask_ne2 = mask_ne3 = 0 or 1 here.  mask_ne2 in {1, ne02}: one mask per
+     * head; mask_ne3 in {1, ne03}: one per batch entry (per-sequence masks of a batched decode).  The row of (query iq1, head iq2,
+     * batch iq3) starts at mask + iq1*nb31 + (iq2 % mask_ne2)*mask_nb2 + (iq3 % mask_ne3)*mask_nb3; every slice has ne31 rows.
+     * Not accepted by the sequence-split entries.  Workspace: b200fa_workspace_size_ext2. */
+    int64_t mask_ne2, mask_ne3, mask_nb2, mask_nb3;
 } b200fa_ext_params;
 int b200fa_flash_attn_ext2(
     const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
@@ -130,6 +137,13 @@ size_t b200fa_workspace_size(
     int q_type, int kv_type,
     int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
     int64_t ne11, int64_t ne12, int64_t ne13, uint32_t flags);
+
+/* The same for b200fa_flash_attn_ext2 with these extensions (mask slices add one table of mask tile classes per slice on the
+ * prefill path); ext == NULL is b200fa_workspace_size. */
+size_t b200fa_workspace_size_ext2(
+    int q_type, int kv_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne11, int64_t ne12, int64_t ne13, const struct b200fa_ext_params* ext, uint32_t flags);
 
 /* cudaMemsetAsync(workspace, 0, bytes) on `stream`; see B200FA_FLAG_WORKSPACE_ZEROED. */
 int b200fa_workspace_init(void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
@@ -155,6 +169,20 @@ int b200fa_flash_attn_partial(
     int64_t nb11, int64_t nb12, int64_t nb13,
     int64_t nb21, int64_t nb22, int64_t nb23,
     int64_t kv_pos0, int64_t n_kv_total,
+    uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
+
+/* The same with the score modifiers of b200fa_flash_attn_ext2 (ALiBi slopes on this slice's mask columns, logit soft-cap); mask
+ * slices are not accepted here.  ext == NULL is b200fa_flash_attn_partial. */
+int b200fa_flash_attn_partial2(
+    const void* q, const void* k, const void* v, const void* mask, float* partial, float scale,
+    int q_type, int kv_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t kv_pos0, int64_t n_kv_total, const struct b200fa_ext_params* ext,
     uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
 
 /* Merge n_parts partial triples per row (partials[p][n_rows][D+2], e.g. the all-gathered per-GPU

@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
     l.oracle_flash_attn_ext.argtypes = ([C.c_void_p] * 5 + [C.c_float] + [C.c_int] * 3 + [C.c_int64] * 23 + [C.c_int] * 3)
     l.oracle_flash_attn_ext2.restype = C.c_int
     l.oracle_flash_attn_ext2.argtypes = ([C.c_void_p] * 5 + [C.c_float] + [C.c_int] * 3 + [C.c_int64] * 23 + [C.c_int] * 3 + [C.c_float] * 2)
+    l.oracle_flash_attn_ext3.restype = C.c_int
+    l.oracle_flash_attn_ext3.argtypes = ([C.c_void_p] * 5 + [C.c_float] + [C.c_int] * 3 + [C.c_int64] * 23 + [C.c_int] * 3 + [C.c_float] * 2 + [C.c_int64] * 4)
     return l
 
 
@@ -103,19 +105,23 @@ def flash_attn_ext(q: View, k: View, v: View, mask: View | None, scale: float, d
                    round_q_f16: bool = False, strict_ref: bool = False, nthreads: int = 0, max_bias: float = 0.0,
                    logit_softcap: float = 0.0) -> np.ndarray:
     """softmax(scale·QKᵀ + mask)·V -> numpy [ne03][n_q][n_head][D]  (flash-llama.h:434 layout).
-    max_bias / logit_softcap: upstream ggml extensions (ALiBi slopes on the mask, tanh soft-cap) — not in the reference."""
+    max_bias / logit_softcap: upstream ggml extensions (ALiBi slopes on the mask, tanh soft-cap) — not in the reference.
+    mask: a 2-D view is the reference's shared mask; a 4-D view [ne33][ne32][rows][n_kv] carries one slice per head (ne32 = n_head or 1)
+    and per batch entry (ne33 = n_batch or 1) — upstream ggml's broadcast, not in the reference either."""
     D, n_q, n_head, n_b = q.ne
     out = np.empty((n_b, n_q, n_head, D), np.float16 if dst_type == TYPE_F16 else np.float32)
     if nthreads <= 0:
         nthreads = os.cpu_count() or 1
-    rc = lib().oracle_flash_attn_ext2(
+    rc = lib().oracle_flash_attn_ext3(
         q.ptr, k.ptr, v.ptr, mask.ptr if mask is not None else None, out.ctypes.data, scale,
         q.type, k.type, dst_type,
         *q.ne, *k.ne,
         mask.ne[1] if mask is not None else 0, mask.nb[1] if mask is not None else 0,
         q.nb[1], q.nb[2], q.nb[3], k.nb[1], k.nb[2], k.nb[3], v.nb[1], v.nb[2], v.nb[3],
         D, n_head, n_q, n_b,
-        int(round_q_f16), int(strict_ref), nthreads, float(max_bias), float(logit_softcap))
+        int(round_q_f16), int(strict_ref), nthreads, float(max_bias), float(logit_softcap),
+        mask.ne[2] if mask is not None else 1, mask.ne[3] if mask is not None else 1,
+        mask.nb[2] if mask is not None else 0, mask.nb[3] if mask is not None else 0)
     if rc != 0:
         raise ValueError(f"oracle_flash_attn_ext rejected the arguments (rc={rc})")
     return out

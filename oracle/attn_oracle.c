@@ -144,6 +144,7 @@ typedef struct {
     int64_t ne0, ne1, ne2, ne3;
     int round_q_f16, strict_ref;
     float max_bias, logit_softcap; /* upstream ggml_flash_attn_ext extensions (0 = off); see oracle_flash_attn_ext2 */
+    int64_t ne32, ne33, nb32, nb33; /* mask slices per head / batch (upstream ggml broadcast; 1, 1 = the reference's shared mask) */
 } oracle_args;
 
 /* widen one K/V row (ne10 elements) to f32 */
@@ -175,7 +176,8 @@ static void attend_head(const oracle_args* a, int64_t iq3, int64_t iq2, float* s
             if (a->round_q_f16) x = h2f(f2h(x)); /* utils.h:10 */
             qrow[i] = x;
         }
-        const uint16_t* mrow = a->mask ? (const uint16_t*)(a->mask + iq1 * a->nb31) : NULL; /* flash-llama.h:151 */
+        const uint16_t* mrow = a->mask ? (const uint16_t*)(a->mask + iq1 * a->nb31 + (iq2 % a->ne32) * a->nb32 + (iq3 % a->ne33) * a->nb33)
+                                       : NULL; /* flash-llama.h:151 (shared mask: ne32 = ne33 = 1) */
         /* ALiBi slope of this head and logit soft-cap — upstream ggml semantics, NOT in the reference (see oracle_flash_attn_ext2) */
         float slope = 1.0f;
         if (a->max_bias > 0.0f) {
@@ -272,6 +274,19 @@ int oracle_flash_attn_ext2(
     int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
     int round_q_f16, int strict_ref, int nthreads, float max_bias, float logit_softcap);
 
+int oracle_flash_attn_ext3(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+    int round_q_f16, int strict_ref, int nthreads, float max_bias, float logit_softcap,
+    int64_t ne32, int64_t ne33, int64_t nb32, int64_t nb33);
+
 int oracle_flash_attn_ext(
     const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
     int q_type, int kv_type, int dst_type,
@@ -301,7 +316,28 @@ int oracle_flash_attn_ext2(
     int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
     int round_q_f16, int strict_ref, int nthreads, float max_bias, float logit_softcap)
 {
+    return oracle_flash_attn_ext3(q, k, v, mask, dst, scale, q_type, kv_type, dst_type, ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13,
+                                  ne31, nb31, nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23, ne0, ne1, ne2, ne3,
+                                  round_q_f16, strict_ref, nthreads, max_bias, logit_softcap, 1, 1, 0, 0);
+}
+
+/* + mask slices: the mask row of (iq1, iq2, iq3) is mask + iq1*nb31 + (iq2 % ne32)*nb32 + (iq3 % ne33)*nb33 (upstream ggml's
+ * broadcast of the mask over heads and batch entries; not in the reference, whose mask is shared: flash-llama.h:151,194) */
+int oracle_flash_attn_ext3(
+    const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
+    int q_type, int kv_type, int dst_type,
+    int64_t ne00, int64_t ne01, int64_t ne02, int64_t ne03,
+    int64_t ne10, int64_t ne11, int64_t ne12, int64_t ne13,
+    int64_t ne31, int64_t nb31,
+    int64_t nb01, int64_t nb02, int64_t nb03,
+    int64_t nb11, int64_t nb12, int64_t nb13,
+    int64_t nb21, int64_t nb22, int64_t nb23,
+    int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+    int round_q_f16, int strict_ref, int nthreads, float max_bias, float logit_softcap,
+    int64_t ne32, int64_t ne33, int64_t nb32, int64_t nb33)
+{
     if (!q || !k || !v || !dst) return -1;
+    if (ne32 < 1 || ne33 < 1) return -1;
     if (ne00 != ne10 || ne00 <= 0 || ne12 <= 0 || ne13 <= 0) return -1;
     if (ne02 % ne12 || ne03 % ne13) return -1;
     if (kv_type == ORACLE_TYPE_Q8_0 && (ne00 % QK8_0)) return -1;
@@ -311,7 +347,7 @@ int oracle_flash_attn_ext2(
         q_type, kv_type, dst_type,
         ne00, ne01, ne02, ne03, ne10, ne11, ne12, ne13, ne31, nb31,
         nb01, nb02, nb03, nb11, nb12, nb13, nb21, nb22, nb23,
-        ne0, ne1, ne2, ne3, round_q_f16, strict_ref, max_bias, logit_softcap };
+        ne0, ne1, ne2, ne3, round_q_f16, strict_ref, max_bias, logit_softcap, ne32, ne33, nb32, nb33 };
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if (nthreads == 1) {

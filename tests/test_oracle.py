@@ -222,3 +222,22 @@ def test_score_modifiers_against_numpy(n_head, max_bias, softcap):
         p = np.exp(s - s.max(axis=1, keepdims=True)); p /= p.sum(axis=1, keepdims=True)
         ref[0, :, h, :] = p @ V[0, h].astype(np.float64)
     assert np.abs(got - ref).max() < 2e-6
+
+
+def test_mask_slices_follow_the_ggml_broadcast_rule():
+    """oracle_flash_attn_ext3: one mask per head / batch entry (upstream ggml's ne32 / ne33 broadcast; the reference's mask is shared,
+    flash-llama.h:151,194).  Cross-checked against float64 numpy; a 4-D mask with ne32 = ne33 = 1 equals the shared 2-D mask."""
+    D, n_q, n_kv, H, Hk, B = 32, 3, 40, 4, 2, 2
+    Q, K, V = synth_qkv(D, n_q, n_kv, H, Hk, n_batch=B)
+    rng = np.random.default_rng(0)
+    for ne33, ne32 in [(B, H), (B, 1), (1, H), (1, 1)]:
+        M = rng.uniform(-1, 1, (ne33, ne32, 32, n_kv)).astype(np.float16)
+        ref = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), oracle.view_of(M), 1 / np.sqrt(D))
+        for b in range(B):
+            for h in range(H):
+                s = (Q[b, h].astype(np.float64) @ K[b, h // 2].astype(np.float64).T) / np.sqrt(D) + M[b % ne33, h % ne32, :n_q].astype(np.float64)
+                p = np.exp(s - s.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+                assert np.abs(p @ V[b, h // 2].astype(np.float64) - ref[b, :, h]).max() < 1e-5
+        if ne32 == ne33 == 1:
+            shared = oracle.flash_attn_ext(oracle.view_of(Q), oracle.view_of(K), oracle.view_of(V), oracle.view_of(np.ascontiguousarray(M[0, 0])), 1 / np.sqrt(D))
+            assert np.array_equal(shared, ref)

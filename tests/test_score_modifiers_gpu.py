@@ -112,3 +112,31 @@ def test_invalid_modifiers():
         P.flash_attn_ext(q, k, k, None, max_bias=-1.0)
     with pytest.raises(P.B200FAError):
         P.flash_attn_ext(q, k, k, None, logit_softcap=float("inf"))
+
+
+@pytest.mark.parametrize("max_bias,softcap", [(8.0, 0.0), (0.0, 30.0), (4.0, 20.0)])
+@pytest.mark.parametrize("n_q,q8", [(1, False), (1, True), (40, False)])
+def test_modifiers_in_the_sequence_split_entry(max_bias, softcap, n_q, q8):
+    """b200fa_flash_attn_partial2: four KV slices with ALiBi / soft-cap, each given its own mask columns, merged = the unsplit result."""
+    import torch
+    P = pkg()
+    D, n_kv, H, Hk = 128, 1024, 8, 2
+    Q, K, V = synth_qkv(D, n_q, n_kv, H, Hk)
+    M = alibi_mask(n_q, n_kv, True)
+    if q8:
+        Kq = oracle.quantize_q8_0(K.astype(np.float32)); Vq = oracle.quantize_q8_0(V.astype(np.float32))
+        kview, vview, k, v = oracle.view_of(Kq, oracle.TYPE_Q8_0), oracle.view_of(Vq, oracle.TYPE_Q8_0), to_dev(Kq), to_dev(Vq)
+    else:
+        kview, vview, k, v = oracle.view_of(K), oracle.view_of(V), to_dev(K), to_dev(V)
+    ref = oracle.flash_attn_ext(oracle.view_of(Q), kview, vview, oracle.view_of(M), 1 / np.sqrt(D), round_q_f16=True, max_bias=max_bias, logit_softcap=softcap)
+    rows = (n_q + 31) // 32 * 32
+    mm = np.zeros((rows, n_kv), np.float16); mm[:n_q] = M
+    q = to_dev(Q)
+    parts = []
+    for i in range(4):
+        sl = slice(i * 256, (i + 1) * 256)
+        parts.append(P.flash_attn_partial(q, k[:, :, sl], v[:, :, sl], to_dev(np.ascontiguousarray(mm[:, sl])), kv_pos0=i * 256, n_kv_total=n_kv,
+                                          max_bias=max_bias, logit_softcap=softcap))
+    out = P.merge_partials(torch.stack(parts))
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy().reshape(ref.shape), ref, f"partial2 max_bias={max_bias} softcap={softcap} n_q={n_q} q8={q8}")
