@@ -9,8 +9,10 @@
 //   item_full / item_empty [2]   the producer warp publishes (work index, KV range, tile classes) of item k in slot k&1;
 //                                the two issuers and the eight softmax warps release the slot when they are done with it
 //   q_empty[t]                   issuer t: every Q_t.K^T of the item has completed -> Q_t may be overwritten
+//   o_full[t]                    issuer t: every P.V of the item has completed -> O_t may be read out (tcgen05.commit)
 //   o_free[t]                    softmax group t: O_t has been read out of TMEM -> the next item's first P.V may overwrite it
-// Every barrier keeps running phase counters across items, and every waiter still observes every phase in order.
+// Every barrier keeps running phase counters across items, and every waiter observes every phase in order — except pv_done[t],
+// which the softmax groups only wait on before a (rare) lazy rescale (see there for why that is unambiguous).
 #pragma once
 #include <string.h>
 
@@ -26,7 +28,7 @@ struct PpShared {
     uint8_t v[2][PF_TILE_BYTES];
     uint8_t stage[8][2][2048];        // epilogue transposition: two buffers of 32 rows x 64 bytes per softmax warp
     uint8_t cls2[2][PP_MAX_KV_TILES]; // per item slot
-    uint64_t q_full[2], q_empty[2], k_full[2], k_empty[2], v_full[2], v_empty[2], pv_done[2], o_free[2];
+    uint64_t q_full[2], q_empty[2], k_full[2], k_empty[2], v_full[2], v_empty[2], pv_done[2], o_full[2], o_free[2];
     uint64_t s_full[2][2], p_full[2][2];
     uint64_t item_full[2], item_empty[2];
     int it_w[2], it_jlo[2], it_jhi[2];
@@ -157,7 +159,7 @@ __device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& 
             for (int j = j_hi - 1; j >= j_lo; j--)
                 if (((sm.cls2[slot][j] >> (2 * t)) & 3) != 2) { j_last = j; break; }
             int pend = -1;
-            // o_free[t] is only used by items in which this query tile has work: those keep the softmax group and this
+            // o_full[t] / o_free[t] are only used by items in which this query tile has work: those keep the softmax group and this
             // issuer in lock step through s_full / p_full.  (An idle softmax group could otherwise run two items — two
             // phases — ahead of its issuer, and a parity wait that is two phases late never returns.)
             bool have_q = false, o_seen = (n_work == 0), first_pv = true;
@@ -219,6 +221,7 @@ __device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& 
                 issue_pv(1);
                 tc_commit(&sm.v_empty[pend]);
             }
+            if (j_last >= 0) tc_commit(&sm.o_full[t]);  // every product of the item has landed: O_t may be read out
             if (tile_valid) {
                 if (!have_q) {  // the tile was loaded but nothing of the KV range is visible to it: hand Q_t straight back
                     mbar_wait(&sm.q_full[t], nq & 1, a.dbg, 4);
@@ -251,7 +254,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1);
             mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 2);  // one arrival per MMA issuer
             mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 2);
-            mbar_init(&sm.pv_done[s], 1); mbar_init(&sm.o_free[s], 4);  // o_free, p_full: one arrival per softmax warp
+            mbar_init(&sm.pv_done[s], 1); mbar_init(&sm.o_full[s], 1); mbar_init(&sm.o_free[s], 4);  // o_free, p_full: one arrival per softmax warp
             for (int h = 0; h < 2; h++) { mbar_init(&sm.s_full[s][h], 1); mbar_init(&sm.p_full[s][h], 4); }
             mbar_init(&sm.item_full[s], 1); mbar_init(&sm.item_empty[s], 10);  // 2 issuers + 8 softmax warps
         }
@@ -296,6 +299,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
         const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
         int it_tot = 0;   // tiles done over all items (phase counter of s_full[t][h])
         int g_tot = 0;    // half tiles done over all items (phase counter of pv_done[t])
+        int n_work = 0;   // items in which this query tile had work (phase counter of o_full[t])
         for (int k = 0;; k++) {
             const int slot = k & 1;
             mbar_wait(&sm.item_full[slot], (k >> 1) & 1, a.dbg, 24);
@@ -380,12 +384,12 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                         for (int i = 0; i < 32; i++) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[q2][i]));
                     const float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
                     const bool need = m_tile > m_ref + PF_RESCALE_THRESHOLD;  // also true for the first finite max
-                    // pv_done(g_tot-1) is observed in every half-iteration (phase rule).  For the first half of an item it was
-                    // observed by the previous item's epilogue, and O_t holds nothing of this item yet.
-                    bool saw_pv = (g == 0);
+                    // O_t holds the sum over the halves before this one; the last of those products must have landed before it is
+                    // rescaled.  pv_done is NOT observed in every half-iteration (that cost ~100 cycles per half): having seen
+                    // s_full of this half, which the issuer committed after P.V(g-2), and with P.V(g) not yet issued, the barrier can only
+                    // be in phase g_tot-1 or g_tot here, so the parity wait for P.V(g-1) is unambiguous.
                     if (g > 0 && __any_sync(0xffffffffu, need)) {
                         mbar_wait(&sm.pv_done[t], (g_tot - 1) & 1, a.dbg, 8);
-                        saw_pv = true;
                         __syncwarp();
                         tc_fence_after();
                         const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.f;
@@ -438,10 +442,6 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                         unpack2(add2(ls2[0], ls2[1]), a0, a1); unpack2(add2(ls2[2], ls2[3]), b0, b1);
                         l += (a0 + a1) + (b0 + b1);
                     }
-                    if (!saw_pv) {
-                        mbar_wait(&sm.pv_done[t], (g_tot - 1) & 1, a.dbg, 10);
-                        __syncwarp();
-                    }
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
@@ -454,7 +454,9 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             if (tl) { tl[1] = clock64(); tl[5] = g; }
             uint32_t o[4][32];
             if (g > 0) {
-                mbar_wait(&sm.pv_done[t], (g_tot - 1) & 1, a.dbg, 9);
+                // (pv_done cannot be used here: after the last half its phase may be g_tot-2, g_tot-1 or g_tot.  o_full has one phase per item.)
+                mbar_wait(&sm.o_full[t], n_work & 1, a.dbg, 9);
+                n_work++;
                 __syncwarp();
                 tc_fence_after();
 #pragma unroll
