@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Summarise .ncu-rep captures (gpurun_out/*.ncu-rep) into small tracked text files under profiles/.
-  python profiles/summarize.py gpurun_out/prof_r1_c2.ncu-rep [...]  -> profiles/<name>.summary.txt"""
+"""Summarise ncu captures into small tracked text files under profiles/: a .ncu-rep, or the `ncu -i x.ncu-rep --page raw --csv`
+export of one (x.raw.csv — what comes back from the GPU box when the reports themselves are too large to carry).
+  python profiles/summarize.py gpurun_out/prof_r1_c2.ncu-rep gpurun_out/prof_r2_c5.raw.csv [...]  -> profiles/<name>.summary.txt"""
 import csv
 import io
 import os
@@ -14,19 +15,20 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
         "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio"]
 
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     for rep in sys.argv[1:]:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         if len(rows) < 3:
             print("no data in", rep); continue
         hdr, units = rows[0], rows[1]
-        name = os.path.splitext(os.path.basename(rep))[0]
+        name = os.path.basename(rep).replace(".raw.csv", "").replace(".ncu-rep", "")
         out = [f"# {name}: ncu --set full --clock-control none (per-launch, cold-cache, serialised)"]
         for r in rows[2:]:
             out.append(f"\nkernel: {r[hdr.index('Kernel Name')]}   grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}")
