@@ -607,7 +607,7 @@ def main():
                          "dispatch": disp, "launches_per_step": nl, "parity": parity_block([(got, ref)], "last kv head of the last sequence, its whole GQA group, every row")}
         one("chunked_prefill_256x32k", 256, 32768, 32, 32, 1, False, False, "256 new queries against a 32K f16 cache, 32 heads (split-KV prefill)")
         one("prefill_2k_q8_0_cache", 2048, 2048, 32, 32, 1, True, True, "C3's shape with q8_0 K/V (dequantised once to f16 workspace copies)")
-        one("burst_8x_gqa4_b8_kv8192", 8, 8192, 32, 8, 8, False, False, "8 query positions x GQA 4 = 32 rows per KV head, batch 8, KV 8192 f16 (virtual KV heads)")
+        one("burst_8x_gqa4_b8_kv8192", 8, 8192, 32, 8, 8, False, False, "8 query positions x GQA 4 = 32 rows per KV head, batch 8, KV 8192 f16 (the group packed into one 128-row tile per KV head, 2 KV segments)")
         return out
 
     def run_ref_gpu():

@@ -133,7 +133,12 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
     const bool kv_ok = sh.kv_type == B200FA_TYPE_F16 || (!no_q8_prefill && (D == 64 || D == 128) && kv16 <= ((size_t)512 << 20));
     // More than 16 query positions: the tensor-core kernel, even when a 128-row tile is mostly padding (n_q = 32 against 8 K keys:
     // 122 us on the 16-row-group fallback, which re-reads K/V per group, vs ~40 us here with the KV range split over the SMs).
-    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && n_q > 16 && D <= 128 && kv_ok &&
+    // 17..128 rows per KV head from a GQA group with few query positions (bursts): the same kernel with the group's q heads packed
+    // into one tile (pp_pack_shift) — one pass over K/V per KV head.
+    const int pack_sh = pp_pack_shift(n_q, n_head, n_head_kv, sh.ext);
+    static const bool no_pack = tune_env("B200FA_NO_PACK") != nullptr;
+    const bool packed_burst = pack_sh > 0 && rows > 16 && !no_pack;
+    if (!force_partial_out && !(flags & B200FA_FLAG_NO_TCGEN05) && (n_q > 16 || packed_burst) && D <= 128 && kv_ok &&
         n_kv <= ((sh.Dr == 0 || sh.Dr == 128) && !sh.ext ? (int64_t)PF_MAX_KV_TILES * PF_BN : (int64_t)PP_MAX_KV_TILES * PF_BN)) {
         pl.kind = kPrefill;
         if (sh.q_type == B200FA_TYPE_F32) pl.qf16_bytes = align_up((size_t)(n_q * n_head * n_batch * 128 * 2), 256);
@@ -144,7 +149,8 @@ Plan make_plan(const Shape& sh, uint32_t flags, int sm_count, bool force_partial
         // item's KV tiles into n_splits segments, each its own work item emitting (O~, m, l) rows, merged by a second launch.
         // Pick the segment count with the shortest makespan (waves / segments) among 2..16 with >= 8 KV tiles per segment and at
         // most 128 MB of partial rows.
-        const int64_t n_items = ((qt + 1) / 2) * n_head * n_batch;
+        const int64_t qt_item = pack_sh ? (n_q + (128 >> pack_sh) - 1) / (128 >> pack_sh) : qt;  // query tiles as the kernel cuts them
+        const int64_t n_items = ((qt_item + 1) / 2) * (pack_sh ? n_head_kv : n_head) * n_batch;
         static const bool no_split = tune_env("B200FA_PREFILL_NO_SPLIT") != nullptr;
         if (!no_split && n_items < sm_count && kt >= 16 && kt <= PP_MAX_KV_TILES && (sh.Dr == 0 || sh.Dr == 128)) {
             const size_t row_bytes = (size_t)(n_q * n_head * n_batch) * (128 + 4) * 4;
@@ -543,7 +549,8 @@ static int attn_common(const void* q, const void* k, const void* v, const void* 
     // KV head into kv_div VIRTUAL heads of gqa / kv_div q heads each, so that a unit has <= 16 rows and the stream kernel applies.
     // K/V are streamed kv_div times, but by CTAs working side by side: the repeats are L2 hits (8 positions x GQA 4, batch 8,
     // KV 8192: 190 us on the 16-row-group fallback -> 134 us).
-    int kv_div = virtual_head_split(ne01, ne02, ne12, ne03);
+    // (Not when the tensor-core kernel takes the burst with the group packed into one tile: one pass over K/V instead of kv_div.)
+    int kv_div = make_plan(sh, flags, di.sm_count, want_partial, false).kind == kPrefill ? 1 : virtual_head_split(ne01, ne02, ne12, ne03);
     if (kv_div > 1) {
         Shape sv = sh;
         sv.n_head_kv = ne12 * kv_div;
@@ -662,7 +669,7 @@ int b200fa_plan(int q_type, int kv_type, int64_t ne00, int64_t ne01, int64_t ne0
     const int64_t row = kv_type == B200FA_TYPE_Q8_0 ? Dp / kQ8BlockElems * kQ8BlockBytes : ne00 * 2;
     Shape sh{q_type, kv_type, Dp, ne01, ne02, ne03, ne11, ne12, row, row * ne11, row * ne11 * ne12, row, row * ne11, row * ne11 * ne12,
              (const void*)256, (const void*)256, 0, ne11, ne00, ne13};
-    int kv_div = virtual_head_split(ne01, ne02, ne12, ne03);
+    int kv_div = make_plan(sh, flags, sm_count, false, false).kind == kPrefill ? 1 : virtual_head_split(ne01, ne02, ne12, ne03);
     if (kv_div > 1) {
         Shape sv = sh;
         sv.n_head_kv = ne12 * kv_div;

@@ -48,11 +48,23 @@ struct PpArgs {
 };
 
 // Role bodies shared by the persistent kernels (one or two softmax threads per query row).
+// iq2: the item's q head — or, with GQA packing, its KV head (the tile holds all q heads of the group)
 __device__ __forceinline__ void pp_decode_item(const FaParams& p, const PfArgs& a, int w, int& qt0, int& iq2, int& iq3) {
-    const int per_pair = p.n_head * p.n_batch;
+    const int heads = a.pack_sh ? p.n_head_kv : p.n_head;
+    const int per_pair = heads * p.n_batch;
     qt0 = 2 * (a.n_q_pairs - 1 - w / per_pair);   // heavy (late) tile pairs first
     const int rem = w % per_pair;
-    iq2 = rem % p.n_head; iq3 = rem / p.n_head;
+    iq2 = rem % heads; iq3 = rem / heads;
+}
+// Q tile load (two 64-column boxes).  Unpacked: tmQ is [D][n_q][head][batch], box 64 x 128 rows.  Packed: tmQ is [D][head][n_q][batch],
+// box 64 x gqa heads x (128 / gqa) positions, which lands position-major / head-minor in the tile.
+__device__ __forceinline__ void pp_load_q(const FaParams& p, const PfArgs& a, void* dst, const CUtensorMap* tmQ, uint64_t* bar, int qt, int iq2, int iq3) {
+    using namespace ptx;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (a.pack_sh) tma_load_4d(reinterpret_cast<uint8_t*>(dst) + c * (PF_TILE_BYTES / 2), tmQ, bar, 64 * c, iq2 << a.pack_sh, qt * a.q_rows, iq3);
+        else tma_load_4d(reinterpret_cast<uint8_t*>(dst) + c * (PF_TILE_BYTES / 2), tmQ, bar, 64 * c, qt * PF_BM, iq2, iq3);
+    }
 }
 
 __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs& pa, PpShared& sm, int lane, const CUtensorMap& tmQ,
@@ -100,14 +112,13 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
         if (lane == 0) mbar_arrive(&sm.item_full[slot]);
         if (w < 0) break;
         if (lane == 0) {
-            const int ik2 = iq2 / p.gqa, ik3 = iq3 / p.rk3;
+            const int ik2 = a.pack_sh ? iq2 : iq2 / p.gqa, ik3 = iq3 / p.rk3;
 #pragma unroll
             for (int t = 0; t < 2; t++) {
                 if (qt0 + t >= a.n_q_tiles) continue;
                 if (nq[t] > 0) mbar_wait(&sm.q_empty[t], (nq[t] - 1) & 1, a.dbg, 21);
                 mbar_arrive_expect_tx(&sm.q_full[t], PF_TILE_BYTES);
-                tma_load_4d(sm.q[t], &tmQ, &sm.q_full[t], 0, (qt0 + t) * PF_BM, iq2, iq3);
-                tma_load_4d(sm.q[t] + PF_TILE_BYTES / 2, &tmQ, &sm.q_full[t], 64, (qt0 + t) * PF_BM, iq2, iq3);
+                pp_load_q(p, a, sm.q[t], &tmQ, &sm.q_full[t], qt0 + t, iq2, iq3);
                 nq[t]++;
             }
             for (int j = lo; j < hi; j++) {
@@ -246,7 +257,6 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     PpShared& sm = *reinterpret_cast<PpShared*>(pp_smem_raw);
     const PfArgs& a = pa.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_pair = p.n_head * p.n_batch;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may take over SMs as this grid's CTAs retire
     if (threadIdx.x == 0) {
@@ -273,12 +283,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // work index -> (first 128-row tile, head, batch); heavy (late) tile pairs first
-    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) {
-        const int item = w / pa.n_seg;
-        qt0 = 2 * (a.n_q_pairs - 1 - item / per_pair);
-        const int rem = item % per_pair;
-        iq2 = rem % p.n_head; iq3 = rem / p.n_head;
-    };
+    auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w / pa.n_seg, qt0, iq2, iq3); };
 
     if (warp >= 8) {
         reg_dec<PF_REGS_OTHER>();
@@ -314,8 +319,8 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
             int qt0, iq2, iq3;
             decode_item(w, qt0, iq2, iq3);
             const int qt = qt0 + t;
-            const int q0 = qt * PF_BM;
-            const int qrow = q0 + r;
+            const int q0 = qt * a.q_rows;                 // first query position of the tile
+            const int qrow = q0 + (r >> a.pack_sh);       // this row's query position (packed: row r = position r >> pack_sh, head r & (gqa - 1))
             // rows past n_q read the last real mask row (their results are never stored): every lane of a warp takes the
             // same path, so the .sync.aligned tcgen05 instructions below always see a converged warp
             const char* mrow = (p.mask != nullptr && !causal) ? p.mask + (int64_t)min(qrow, p.n_q - 1) * p.nb31 + (EXT ? fa_mask_slice_off(p, iq2, iq3) : 0) : nullptr;
@@ -480,7 +485,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                 // one lane hands the 32 x 64-byte box to the TMA engine: the store to HBM is asynchronous, rows past n_q are
                 // clipped by the tensor map, and the warp only waits until the engine has READ the staging buffer.
                 const bool f32out = partial || p.dst_type == B200FA_TYPE_F32;
-                const int row0 = q0 + (warp & 3) * 32;
+                const int row0 = q0 + (((warp & 3) * 32) >> a.pack_sh);  // first query position of this warp's 32 rows
                 // 16 f32 or 32 f16 columns = 64 bytes per pass; columns past the real head size are never stored.  Partials: a ninth
                 // pass carries (m in natural-log units, l) in columns D, D+1 (the box is clipped to the D + 4 columns of a record).
                 const int n_pass = partial ? 9 : (p.Dr * (f32out ? 4 : 2) + 63) >> 6;
@@ -515,7 +520,8 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&tmO, stg, pass * (f32out ? 16 : 32), iq2, row0, c3);
+                        // box: 64 bytes x 1 head x 32 positions — packed: x gqa heads x 32 / gqa positions, the order of the warp's rows
+                        tma_store_4d(&tmO, stg, pass * (f32out ? 16 : 32), iq2 << a.pack_sh, row0, c3);
                         bulk_commit();
                     }
                 }
@@ -546,6 +552,22 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     }
 }
 
+// GQA packing: log2 of the q heads that share one 128-row tile, or 0.  It pays when the q heads of a group would otherwise each
+// occupy their own, mostly empty, tile and stream the group's K/V once per head: 8 query positions x GQA 4 (speculative decoding,
+// small prefill chunks) is ONE quarter-filled tile per KV head instead of four 6 %-filled ones.  Power-of-two groups up to 32 heads
+// (a warp's 32 rows must be whole positions for the output box); not with the ext2 modifiers (their slopes / mask slices are per item).
+inline int pp_pack_shift(int64_t n_q, int64_t n_head, int64_t n_head_kv, bool ext) {
+    if (n_head_kv <= 0 || n_head % n_head_kv) return 0;
+    const int64_t gqa = n_head / n_head_kv;
+    if (ext || gqa < 2 || gqa > 32 || (gqa & (gqa - 1))) return 0;
+    const int64_t np = PF_BM / gqa;
+    const int64_t pairs_packed = ((n_q + np - 1) / np + 1) / 2, pairs_plain = ((n_q + PF_BM - 1) / PF_BM + 1) / 2;
+    if (pairs_packed >= pairs_plain * gqa) return 0;  // no fewer passes over K/V
+    int sh = 0;
+    while ((1 << sh) < gqa) sh++;
+    return sh;
+}
+
 // n_seg > 1: split-KV prefill — `part` ([n_seg][total_rows][D + 4] f32, in the workspace) receives the segments' partial rows and
 // fa_combine_pad merges them into dst in a second launch.
 inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_bytes, unsigned int* counters, int sm_count,
@@ -569,14 +591,18 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     }
     PpArgs pa{};
     PfArgs& a = pa.f;
-    a.n_q_tiles = (p.n_q + PF_BM - 1) / PF_BM;
+    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0 || p.m_ne2 * p.m_ne3 > 1;  // ext2 score modifiers / mask slices: their own instantiation
+    a.pack_sh = pp_pack_shift(p.n_q, p.n_head, p.n_head_kv, ext);
+    a.q_rows = PF_BM >> a.pack_sh;
+    a.cls_q_tiles = (p.n_q + PF_BM - 1) / PF_BM;
+    a.n_q_tiles = (p.n_q + a.q_rows - 1) / a.q_rows;
     a.n_kv_tiles = (p.n_kv + PF_BN - 1) / PF_BN;
     a.n_q_pairs = (a.n_q_tiles + 1) / 2;
     a.inv_scale = 1.0f / p.scale;
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {
         uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
-        fa_mask_classify<<<dim3(a.n_kv_tiles, a.n_q_tiles, p.m_ne2 * p.m_ne3), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2,
+        fa_mask_classify<<<dim3(a.n_kv_tiles, a.cls_q_tiles, p.m_ne2 * p.m_ne3), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2,
                                                                                               p.m_ne2, p.nb32, p.nb33);
         n++;
         a.cls = cls;
@@ -584,10 +610,20 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     }
     if (n_seg < 1 || (n_seg > 1 && (part == nullptr || p.Dr != PF_D))) return B200FA_ERR_INVALID;
     pa.n_seg = n_seg;
-    pa.n_items = a.n_q_pairs * p.n_head * p.n_batch * n_seg;
+    pa.n_items = a.n_q_pairs * (a.pack_sh ? p.n_head_kv : p.n_head) * p.n_batch * n_seg;
     pa.counters = counters;
     CUtensorMap tq, tk, tv;
-    if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3, 128, Dr)) return B200FA_ERR_CUDA;
+    if (a.pack_sh) {  // Q as [D][head][n_q][batch]: a box of 64 columns x gqa heads x 128 / gqa positions is one packed tile half
+        PFN_encodeTiled enc = get_encode_tiled();
+        if (!enc) return B200FA_ERR_CUDA;
+        cuuint64_t dims[4] = {(cuuint64_t)Dr, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch};
+        cuuint64_t strides[3] = {(cuuint64_t)qnb2, (cuuint64_t)qnb1, (cuuint64_t)qnb3};
+        cuuint32_t box[4] = {64, (cuuint32_t)(1 << a.pack_sh), (cuuint32_t)a.q_rows, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(qbase), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return B200FA_ERR_CUDA;
+    } else if (!make_tile_map(&tq, qbase, p.n_q, p.n_head, p.n_batch, qnb1, qnb2, qnb3, 128, Dr)) return B200FA_ERR_CUDA;
     if (!make_tile_map(&tk, p.k, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb11, p.nb12, p.nb13, 128, Dr)) return B200FA_ERR_CUDA;
     if (!make_tile_map(&tv, p.v, p.n_kv, p.n_head_kv, p.n_batch_kv, p.nb21, p.nb22, p.nb23, 128, Dr)) return B200FA_ERR_CUDA;
     CUtensorMap to;
@@ -599,7 +635,7 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
         const cuuint64_t rowlen = n_seg > 1 ? PF_D + 4 : Dr;  // partial records: O~[D], m, l, 2 unused; dim 3 = segment * n_batch + batch
         cuuint64_t dims[4] = {rowlen, (cuuint64_t)p.n_head, (cuuint64_t)p.n_q, (cuuint64_t)p.n_batch * n_seg};
         cuuint64_t strides[3] = {rowlen * es, (cuuint64_t)p.n_head * rowlen * es, (cuuint64_t)p.n_q * p.n_head * rowlen * es};
-        cuuint32_t box[4] = {(cuuint32_t)(64 / es), 1, 32, 1};
+        cuuint32_t box[4] = {(cuuint32_t)(64 / es), (cuuint32_t)(1 << a.pack_sh), (cuuint32_t)(32 >> a.pack_sh), 1};  // a warp's 32 rows
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&to, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, n_seg > 1 ? (void*)part : p.dst, dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -609,7 +645,6 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     constexpr size_t smem_bytes = sizeof(PpShared);
     static_assert(smem_bytes <= 227 * 1024, "prefill shared memory budget");
     static const int poly = tune_env("B200FA_POLY") ? atoi(tune_env("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
-    const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0 || p.m_ne2 * p.m_ne3 > 1;  // ext2 score modifiers / mask slices: their own instantiation
 #ifdef B200FA_TUNING
     auto kern = ext ? fa_prefill_persistent<2, true>
                     : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));

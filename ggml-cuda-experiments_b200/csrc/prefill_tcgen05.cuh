@@ -59,9 +59,14 @@ struct __align__(1024) PfShared {
 };
 
 struct PfArgs {
-    const uint8_t* cls;        // [n_q_tiles][n_kv_tiles] 128x128 tile classes from the mask scan, or null
+    const uint8_t* cls;        // [cls_q_tiles][n_kv_tiles] classes of the 128-position x 128-key mask tiles from the mask scan, or null
     int n_q_tiles, n_kv_tiles; // 128-row / 128-key tiles
     int n_q_pairs;             // CTAs per (head, batch)
+    // GQA packing (persistent kernel only; pack_sh = 0 elsewhere): the 2^pack_sh q heads of a KV head share one 128-row tile,
+    // row r = position r >> pack_sh, head r & (2^pack_sh - 1); a tile then covers q_rows = 128 >> pack_sh query positions.
+    int pack_sh;
+    int q_rows;                // query positions per tile (128 unless packed)
+    int cls_q_tiles;           // rows of the class table: ceil(n_q / 128)
     float inv_scale;           // 1/scale (mask values are folded into raw scores)
     unsigned long long* dbg;   // timeout codes (mapped host memory), may be null
     float* dump;               // diagnostics, may be null
@@ -77,13 +82,15 @@ __device__ __forceinline__ int pf_tile_class(const FaParams& p, const PfArgs& a,
     if (kv0 >= p.n_kv || qt >= a.n_q_tiles) return 2;
     int c = (kv0 + PF_BN > p.n_kv) ? 1 : 0;
     if (causal) {
-        const int64_t q0 = (int64_t)qt * PF_BM;
+        const int64_t q0 = (int64_t)qt * a.q_rows;
         const int64_t first_lim = q0 + p.causal_off;
-        const int64_t last_lim = min(q0 + PF_BM - 1, (int64_t)p.n_q - 1) + p.causal_off;
+        const int64_t last_lim = min(q0 + a.q_rows - 1, (int64_t)p.n_q - 1) + p.causal_off;
         if (kv0 > last_lim) return 2;
         if (kv0 + PF_BN - 1 > first_lim) c = 1;
     } else if (a.cls != nullptr) {
-        const int u = a.cls[((int64_t)slice * a.n_q_tiles + qt) * a.n_kv_tiles + j];
+        // (a packed tile lies inside one 128-position block of the scan: the block's class is exact for "nothing visible" /
+        //  "everything visible" and conservative — mixed — otherwise)
+        const int u = a.cls[((int64_t)slice * a.cls_q_tiles + ((int64_t)qt * a.q_rows) / PF_BM) * a.n_kv_tiles + j];
         if (u == 2) return 2;
         if (u == 1) c = 1;
     } else if (p.mask != nullptr) {
@@ -725,6 +732,7 @@ inline int launch_prefill_tcgen05(const FaParams& p, char* ws, size_t qf16_bytes
     a.n_q_tiles = (p.n_q + PF_BM - 1) / PF_BM;
     a.n_kv_tiles = (p.n_kv + PF_BN - 1) / PF_BN;
     a.n_q_pairs = (a.n_q_tiles + 1) / 2;
+    a.pack_sh = 0; a.q_rows = PF_BM; a.cls_q_tiles = a.n_q_tiles;
     a.inv_scale = 1.0f / p.scale;
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {

@@ -76,11 +76,14 @@ int b200fa_version(void); /* major*10000 + minor*100 + patch */
  * Dispatch (all on the GPU):
  *   n_q <= 16, rows per KV head (n_q * n_head/n_head_kv) <= 16
  *                      -> stream-K decode kernel: TMA-fed ring, mma.sync fragments, split-KV merged in the same launch (HBM-bound)
- *   n_q <= 16, 17..128 rows under GQA
- *                      -> the same kernel over virtual KV heads of <= 16 rows each
+ *   n_q <= 16, more than 16 rows under GQA with a power-of-two group of 2..32 q heads
+ *                      -> the tile kernel below with the group's q heads PACKED into one 128-row tile (row = position x head):
+ *                         one pass over K/V per KV head
+ *   n_q <= 16, 17..128 rows under GQA with any other group size (or with the ext2 modifiers)
+ *                      -> the stream kernel over virtual KV heads of <= 16 rows each
  *   n_q > 16           -> tcgen05/TMEM/TMA tile kernel (prefill; tensor-bound); q8_0 K/V are dequantised once to f16 workspace copies;
  *                         with fewer work items than SMs and a long KV range the KV tiles are split into segments merged by a
- *                         second launch
+ *                         second launch; under GQA (power-of-two groups) tiles are packed whenever that saves passes over K/V
  *   anything else (more than 128 rows from <= 16 positions, scale <= 0, odd q8_0 alignments, sequences beyond the tile schedule)
  *                      -> the register-streaming kernel over 16-row groups
  * Requirements: head size D = ne00: any multiple of 8 up to 128 with f16 K/V (64 and 128 run natively; the others run

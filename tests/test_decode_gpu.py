@@ -383,14 +383,18 @@ def test_graph_replay_back_to_back_calls_share_a_workspace():
 
 @pytest.mark.parametrize("n_q,H,Hk,B,n_kv,kind,q8", [
     (8, 32, 8, 2, 1500, "causal", False), (5, 16, 2, 1, 3000, "noise", False), (16, 8, 2, 3, 777, "causal", False),
-    (4, 32, 4, 1, 2048, "zeros", True), (9, 12, 3, 1, 1000, "causal", False), (3, 24, 3, 2, 640, "none", True)])
-def test_gqa_bursts_17_to_64_rows_use_the_stream_kernel(n_q, H, Hk, B, n_kv, kind, q8):
-    """A burst of query positions under GQA (17..64 rows per KV head): every KV head is split into virtual heads of <= 16 rows."""
+    (4, 32, 4, 1, 2048, "zeros", True), (9, 12, 3, 1, 1000, "causal", False), (3, 24, 3, 2, 640, "none", True),
+    (4, 12, 2, 2, 1500, "causal", False), (3, 36, 3, 1, 900, "noise", False), (5, 10, 2, 1, 2048, "causal", True)])
+def test_gqa_bursts_17_to_64_rows(n_q, H, Hk, B, n_kv, kind, q8):
+    """A burst of query positions under GQA (17..64 rows per KV head).  Power-of-two groups: the tensor-core kernel with the group's q
+    heads packed into one 128-row tile (one pass over K/V per KV head).  Other group sizes (6, 12, 5 here): every KV head is split
+    into virtual heads of <= 16 rows for the stream kernel."""
     Q, K, V = synth_qkv(128, n_q, n_kv, H, Hk, n_batch=B)
     mask = make_mask(kind, n_q, n_kv)
     flags = pkg().FLAG_CAUSAL if kind == "causal" else 0
     run_both(Q, K, V, mask, flags=flags, q8=q8, mask_pad=32 if mask is not None else None)
-    assert pkg().last_dispatch() == "decode_stream", pkg().last_dispatch()
+    gqa = H // Hk
+    assert pkg().last_dispatch() == ("prefill_tcgen05" if gqa & (gqa - 1) == 0 else "decode_stream"), pkg().last_dispatch()
     a, _ = run_both(Q, K, V, mask, flags=flags, q8=q8, cache_view=not q8, dst_f16=True)
 
 

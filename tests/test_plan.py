@@ -34,13 +34,17 @@ def test_configs():
 def test_dispatch_boundaries():
     p = P()
     assert plan(F32, F16, 128, 16, 8, 1, 4096, 8).kind == p.PLAN_STREAM          # 16 rows per KV head: still the stream kernel
-    b = plan(F32, F16, 128, 8, 32, 8, 8192, 8)                                    # 8 positions x GQA 4 = 32 rows: virtual heads
+    b = plan(F32, F16, 128, 8, 32, 8, 8192, 8)                                    # 8 positions x GQA 4 = 32 rows: one packed tile per KV head,
+    assert b.kind == p.PLAN_PREFILL and b.kv_div == 1 and b.n_splits == 2         # 64 items x 2 KV segments
+    b = plan(F32, F16, 128, 16, 16, 1, 4096, 2)                                   # 16 x GQA 8 = 128 rows: a full packed tile
+    assert b.kind == p.PLAN_PREFILL and b.kv_div == 1
+    b = plan(F32, F16, 128, 8, 32, 8, 8192, 8, flags=2)                           # B200FA_FLAG_NO_TCGEN05: virtual heads on the stream kernel
     assert b.kind == p.PLAN_STREAM and b.kv_div == 2
-    b = plan(F32, F16, 128, 5, 16, 1, 3000, 2)                                    # 5 x GQA 8 = 40 rows -> 4 virtual heads of 10 rows
-    assert b.kind == p.PLAN_STREAM and b.kv_div == 4
-    b = plan(F32, F16, 128, 16, 16, 1, 4096, 2)                                   # 16 x GQA 8 = 128 rows -> 8 virtual heads of 16 rows
-    assert b.kind == p.PLAN_STREAM and b.kv_div == 8
-    assert plan(F32, F16, 128, 16, 32, 1, 4096, 2).kind == p.PLAN_ROWS16          # 256 rows from 16 positions: the 16-row kernel
+    b = plan(F32, F16, 128, 5, 12, 1, 3000, 2)                                    # 5 x GQA 6 = 30 rows (not a power of two) -> 2 virtual heads of 15 rows
+    assert b.kind == p.PLAN_STREAM and b.kv_div == 2
+    b = plan(F32, F16, 128, 16, 24, 1, 4096, 2)                                   # 16 x GQA 12 = 192 rows: beyond the virtual heads
+    assert b.kind == p.PLAN_ROWS16
+    assert plan(F32, F16, 128, 16, 32, 1, 4096, 2).kind == p.PLAN_PREFILL         # 16 x GQA 16 = 256 rows: two packed tiles (one item) per KV head
     assert plan(F32, F16, 128, 17, 8, 1, 4096, 8).kind == p.PLAN_PREFILL          # more than 16 positions: the tile kernel
     assert plan(F32, F16, 128, 17, 8, 1, 4096, 8, flags=2).kind == p.PLAN_ROWS16  # ... unless B200FA_FLAG_NO_TCGEN05
     assert plan(F32, F16, 80, 1, 8, 1, 1000, 8).kind == p.PLAN_STREAM             # padded head sizes
