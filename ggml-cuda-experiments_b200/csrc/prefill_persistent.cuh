@@ -580,12 +580,12 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     int n = 0;
     const void* qbase = p.q;
     int64_t qnb1 = p.nb01, qnb2 = p.nb02, qnb3 = p.nb03;
+    PfPrepArgs prep{};  // the helper launch in front of the attention kernel: Q conversion and / or mask scan
     if (p.q_type == B200FA_TYPE_F32) {
         __half* q16 = reinterpret_cast<__half*>(ws);
         const int64_t work = p.total_rows * (Dr / 8);
-        fa_q_to_f16<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p.q, q16, Dr, p.n_q, p.n_head, p.total_rows, p.nb01, p.nb02,
-                                                                   p.nb03);
-        n++;
+        prep.q = p.q; prep.q16 = q16; prep.D = Dr; prep.n_q = p.n_q; prep.n_head = p.n_head; prep.total_rows = p.total_rows;
+        prep.nb01 = p.nb01; prep.nb02 = p.nb02; prep.nb03 = p.nb03; prep.q_blocks = (unsigned)((work + 255) / 256);
         qbase = q16;
         qnb1 = Dr * 2; qnb2 = (int64_t)p.n_q * Dr * 2; qnb3 = (int64_t)p.n_head * p.n_q * Dr * 2;
     }
@@ -602,11 +602,17 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     a.dbg = pf_debug().dbg; a.dump = pf_debug().dump; a.dump_cta = pf_debug().dump_cta;
     if (p.mask != nullptr && !p.causal) {
         uint8_t* cls = reinterpret_cast<uint8_t*>(ws + qf16_bytes);
-        fa_mask_classify<<<dim3(a.n_kv_tiles, a.cls_q_tiles, p.m_ne2 * p.m_ne3), 256, 0, st>>>(p.mask, p.nb31, p.n_q, p.n_kv, a.n_kv_tiles, cls, counters + 2,
-                                                                                              p.m_ne2, p.nb32, p.nb33);
-        n++;
+        prep.mask = p.mask; prep.nb31 = p.nb31; prep.n_q = p.n_q; prep.n_kv = p.n_kv; prep.n_kv_tiles = a.n_kv_tiles; prep.cls_q_tiles = a.cls_q_tiles;
+        prep.cls = cls; prep.not_causal = counters + 2; prep.m_ne2 = p.m_ne2; prep.nb32 = p.nb32; prep.nb33 = p.nb33;
         a.cls = cls;
         pa.detect_causal = 1;
+    }
+    {
+        const unsigned cls_blocks = prep.mask ? (unsigned)(a.n_kv_tiles * a.cls_q_tiles * p.m_ne2 * p.m_ne3) : 0u;
+        if (prep.q_blocks + cls_blocks > 0) {
+            fa_prefill_prep<<<prep.q_blocks + cls_blocks, 256, 0, st>>>(prep);
+            n++;
+        }
     }
     if (n_seg < 1 || (n_seg > 1 && (part == nullptr || p.Dr != PF_D))) return B200FA_ERR_INVALID;
     pa.n_seg = n_seg;

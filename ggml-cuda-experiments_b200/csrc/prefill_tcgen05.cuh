@@ -580,12 +580,10 @@ fa_prefill_tcgen05(const __grid_constant__ FaParams p, const __grid_constant__ P
 // elsewhere": a caller that passes the usual causal mask tensor without B200FA_FLAG_CAUSAL still gets the synthesised
 // mask (no per-element mask reads in the attention kernel).
 // blockIdx.z = mask slice (head + m_ne2 * batch): its base is mask + (z % m_ne2) * nb32 + (z / m_ne2) * nb33, its classes follow those of slice z - 1
-__global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__ mask, int64_t nb31, int n_q, int n_kv,
-                                                        int n_kv_tiles, uint8_t* __restrict__ cls, unsigned int* not_causal,
-                                                        int m_ne2 = 1, int64_t nb32 = 0, int64_t nb33 = 0) {
-    const int j = blockIdx.x, qt = blockIdx.y;
-    mask += (int64_t)(blockIdx.z % m_ne2) * nb32 + (int64_t)(blockIdx.z / m_ne2) * nb33;
-    cls += (int64_t)blockIdx.z * gridDim.y * n_kv_tiles;
+__device__ __forceinline__ void pf_classify_block(int j, int qt, int z, int n_q_tiles_grid, const char* __restrict__ mask, int64_t nb31, int n_q, int n_kv,
+                                                  int n_kv_tiles, uint8_t* __restrict__ cls, unsigned int* not_causal, int m_ne2, int64_t nb32, int64_t nb33) {
+    mask += (int64_t)(z % m_ne2) * nb32 + (int64_t)(z / m_ne2) * nb33;
+    cls += (int64_t)z * n_q_tiles_grid * n_kv_tiles;
     const int off = n_kv - n_q;
     int has_zero = 0, has_ninf = 0, has_other = 0, deviates = 0;
     const bool vec = ((((uintptr_t)mask | (uintptr_t)nb31) & 15) == 0) && (j + 1) * PF_BN <= n_kv;  // (mask already points at the slice)
@@ -637,12 +635,17 @@ __global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__
         if (deviates && not_causal != nullptr) atomicAdd(not_causal, 1u);
     }
 }
+__global__ void __launch_bounds__(256) fa_mask_classify(const char* __restrict__ mask, int64_t nb31, int n_q, int n_kv,
+                                                        int n_kv_tiles, uint8_t* __restrict__ cls, unsigned int* not_causal,
+                                                        int m_ne2 = 1, int64_t nb32 = 0, int64_t nb33 = 0) {
+    pf_classify_block(blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, mask, nb31, n_q, n_kv, n_kv_tiles, cls, not_causal, m_ne2, nb32, nb33);
+}
 
 // f32 Q (any ggml strides) -> dense f16 [batch][head][q][D]; same rounding as the reference (flash-llama.h:80)
-__global__ void __launch_bounds__(256) fa_q_to_f16(const char* __restrict__ q, __half* __restrict__ out, int D, int n_q, int n_head,
-                                                   int64_t total_rows, int64_t nb01, int64_t nb02, int64_t nb03) {
+__device__ __forceinline__ void pf_q_to_f16_block(int64_t block, const char* __restrict__ q, __half* __restrict__ out, int D, int n_q, int n_head,
+                                                  int64_t total_rows, int64_t nb01, int64_t nb02, int64_t nb03) {
     const int chunks = D / 8;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = block * blockDim.x + threadIdx.x;
     if (idx >= total_rows * chunks) return;
     const int64_t row = idx / chunks;
     const int ch = (int)(idx % chunks);
@@ -652,6 +655,26 @@ __global__ void __launch_bounds__(256) fa_q_to_f16(const char* __restrict__ q, _
     const float4 x = src[0], y = src[1];
     *reinterpret_cast<uint4*>(out + row * D + ch * 8) =
         make_uint4(pack_half2(x.x, x.y), pack_half2(x.z, x.w), pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+}
+__global__ void __launch_bounds__(256) fa_q_to_f16(const char* __restrict__ q, __half* __restrict__ out, int D, int n_q, int n_head,
+                                                   int64_t total_rows, int64_t nb01, int64_t nb02, int64_t nb03) {
+    pf_q_to_f16_block(blockIdx.x, q, out, D, n_q, n_head, total_rows, nb01, nb02, nb03);
+}
+
+// Both helpers of a call in ONE launch (the reference's own call has an f32 Q and a mask tensor: two tiny kernels in front of the
+// attention kernel cost two kernel boundaries): blocks [0, q_blocks) convert Q, the rest classify one mask tile each.
+struct PfPrepArgs {
+    const char* q; __half* q16; int D, n_q, n_head; int64_t total_rows, nb01, nb02, nb03; unsigned q_blocks;
+    const char* mask; int64_t nb31; int n_kv, n_kv_tiles, cls_q_tiles; uint8_t* cls; unsigned int* not_causal; int m_ne2; int64_t nb32, nb33;
+};
+__global__ void __launch_bounds__(256) fa_prefill_prep(const PfPrepArgs a) {
+    if (blockIdx.x < a.q_blocks) {
+        pf_q_to_f16_block(blockIdx.x, a.q, a.q16, a.D, a.n_q, a.n_head, a.total_rows, a.nb01, a.nb02, a.nb03);
+        return;
+    }
+    const unsigned b = blockIdx.x - a.q_blocks;
+    const int j = (int)(b % (unsigned)a.n_kv_tiles), qt = (int)((b / (unsigned)a.n_kv_tiles) % (unsigned)a.cls_q_tiles), z = (int)(b / ((unsigned)a.n_kv_tiles * (unsigned)a.cls_q_tiles));
+    pf_classify_block(j, qt, z, a.cls_q_tiles, a.mask, a.nb31, a.n_q, a.n_kv, a.n_kv_tiles, a.cls, a.not_causal, a.m_ne2, a.nb32, a.nb33);
 }
 
 // ---------------- host side ----------------
