@@ -730,7 +730,8 @@ int b200fa_flash_attn_partial2(const void* q, const void* k, const void* v, cons
 
 size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D) {
     if (world < 1 || n_rows < 1 || D < 1) return 0;
-    return (size_t)kXchgHeader + (1 + 2 * (size_t)world) * (size_t)n_rows * (size_t)(D + 2) * 4;
+    const size_t n_floats = (size_t)n_rows * (size_t)(D + 2);
+    return (size_t)xchg_ll_offset(world, (int64_t)n_floats) + 2 * (size_t)world * n_floats * 8;  // header, staging, gathered x 2, flag-in-data x 2
 }
 
 int b200fa_flash_attn_partial_scatter(const void* q, const void* k, const void* v, const void* mask, float scale,

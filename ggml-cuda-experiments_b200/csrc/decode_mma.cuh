@@ -739,12 +739,31 @@ __global__ void __launch_bounds__(D) fa_combine_pad(const float* __restrict__ pa
 //                   [16] scatter block counter, [17] merge block counter (self-resetting), [32] steps completed by THIS rank
 //   staging   [row][D + 2] f32 : this rank's triples of the current step (written by the attention kernel)
 //   gathered  [gen][rank][row][D + 2] f32 : two generations (step parity)
+//   gathered, flag-in-data [gen][rank][row][D + 2] x {f32 value, u32 tag} : the fused one-kernel step (b200fa_flash_attn_seqpar)
+//       publishes every float as ONE 8-byte store carrying the value and the step's tag; a reader polls the element itself until
+//       the tag matches.  No fence, no arrival counter, no second NVLink round trip (the idea of NCCL's LL protocol).
 // The step number lives on the device, so a step is a fixed sequence of launches that can be captured in a CUDA graph.
 constexpr int kXchgHeader = 256;
+// byte offset of the flag-in-data area
+__host__ __device__ inline int64_t xchg_ll_offset(int world, int64_t n_floats) { return (int64_t)kXchgHeader + (1 + 2 * (int64_t)world) * n_floats * 4; }
 // header words (u32): [0] arrivals of all ranks (monotonic), [16] [17] local block counters, [32] steps completed on this rank,
 // [33] error flag: 1 = a wait for the peers timed out (the step's output was NOT written; b200fa_peer_status / b200fa_peer_reset),
 // [34] timeout of those waits in milliseconds (0 = kXchgDefaultTimeoutMs; b200fa_peer_set_timeout)
-constexpr int kXchgErrWord = 33, kXchgTimeoutWord = 34;
+// [35] epoch: incremented by b200fa_peer_reset (never cleared), part of the flag-in-data tag so that values of an abandoned step
+//      sequence can never be taken for current ones
+constexpr int kXchgErrWord = 33, kXchgTimeoutWord = 34, kXchgEpochWord = 35;
+// tag of a step: never 0 (the buffer starts zero-filled), never equal to the tag two steps earlier (the slot's previous contents)
+__device__ __forceinline__ unsigned int xchg_ll_tag(const unsigned int* hdr, unsigned int step) { return 0x80000000u | ((hdr[kXchgEpochWord] & 0x7fu) << 24) | (step & 0xffffffu); }
+// one aligned 64-bit access per element: value in the low word, tag in the high word (single-copy atomic)
+__device__ __forceinline__ void st_ll(void* p, float v, unsigned int tag) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const void* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return make_uint2((unsigned int)w, (unsigned int)(w >> 32));
+}
 constexpr unsigned int kXchgDefaultTimeoutMs = 4000;
 
 __device__ __forceinline__ unsigned long long xchg_now_ns() {
@@ -779,7 +798,8 @@ __global__ void fa_xchg_set_word(char* xchg, int word, unsigned int value) { rei
 // header back to its initial state (steps, arrivals, counters, error flag), keeping the configured timeout
 __global__ void fa_xchg_reset(char* xchg) {
     unsigned int* hdr = reinterpret_cast<unsigned int*>(xchg);
-    if (threadIdx.x < kXchgHeader / 4 && threadIdx.x != kXchgTimeoutWord) hdr[threadIdx.x] = 0u;
+    if (threadIdx.x < kXchgHeader / 4 && threadIdx.x != kXchgTimeoutWord && threadIdx.x != kXchgEpochWord) hdr[threadIdx.x] = 0u;
+    if (threadIdx.x == kXchgEpochWord) hdr[kXchgEpochWord] = (hdr[kXchgEpochWord] + 1u) & 0x7fu;
 }
 
 // Copies this rank's staged triples into slot `rank` of every rank's gathered area (its own included) with plain stores —

@@ -797,62 +797,84 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     // ---- fused sequence-parallel step: where the unit triples go, and what the last CTA of the rank does ----
     int units_done = 0;  // units whose final triple this CTA has written
     unsigned int sp_step = 0;
-    int64_t sp_gen_off = 0;
     const int64_t sp_n_floats = p.total_rows * (D + 2);
+    if (a.peers != nullptr) sp_step = reinterpret_cast<const unsigned int*>(a.peers[a.rank])[32] + 1;  // this rank's step in progress (see decode_mma.cuh)
+    // Flag-in-data exchange: every float of a unit's triple goes to every rank as one 8-byte store {value, tag of this step} into
+    // the rank's flag-in-data area (decode_mma.cuh); nothing is fenced and nothing is counted.  A reader polls the elements it
+    // needs until their tags match, which is all the synchronisation there is: one NVLink traversal between the last local
+    // chunk and the merge instead of stores + system fence + counter increment + counter poll.
+    unsigned int sp_tag = 0;
+    int64_t sp_ll_off = 0;
     if (a.peers != nullptr) {
-        sp_step = reinterpret_cast<const unsigned int*>(a.peers[a.rank])[32] + 1;  // this rank's step in progress (see decode_mma.cuh)
-        sp_gen_off = (int64_t)(sp_step & 1u) * a.world * sp_n_floats;
+        sp_tag = xchg_ll_tag(reinterpret_cast<const unsigned int*>(a.peers[a.rank]), sp_step);
+        sp_ll_off = xchg_ll_offset(a.world, sp_n_floats);
     }
     auto emit_triple = [&](int64_t orow, int d, float acc, bool with_ml, float m_nat, float l_sum) {
-        const int64_t off = sp_n_floats + sp_gen_off + (int64_t)a.rank * sp_n_floats + orow * (D + 2);
-        for (int pr = 0; pr < a.world; pr++) {  // plain stores; over NVLink for the peers
-            float* out = reinterpret_cast<float*>(a.peers[pr] + kXchgHeader) + off;
-            out[d] = acc;
-            if (with_ml) { out[D] = m_nat; out[D + 1] = l_sum; }
+        const int64_t off = ((int64_t)(sp_step & 1u) * a.world + a.rank) * sp_n_floats + orow * (D + 2);
+        for (int pr = 0; pr < a.world; pr++) {  // over NVLink for the peers
+            uint2* out = reinterpret_cast<uint2*>(a.peers[pr] + sp_ll_off) + off;
+            st_ll(out + d, acc, sp_tag);
+            if (with_ml) { st_ll(out + D, m_nat, sp_tag); st_ll(out + D + 1, l_sum, sp_tag); }
         }
     };
     auto finish_seqpar = [&]() {
         if (a.peers == nullptr || units_done == 0) return;  // (uniform per CTA) only CTAs that published a unit have anything to do
         unsigned int* hdr = reinterpret_cast<unsigned int*>(a.peers[a.rank]);
-        __threadfence_system();
+        if (threadIdx.x == 0) s_flag[2] = (int)atomicAdd(hdr + 16, (unsigned int)units_done);   // this CTA's share of the merge ~ units published
+        if (threadIdx.x == 0) s_flag[3] = 1;
         bar_consumers();
-        if (threadIdx.x == 0) {
-            const unsigned int old = atomicAdd(hdr + 16, (unsigned int)units_done);
-            s_flag[2] = (int)old;
-            if (old + (unsigned int)units_done == (unsigned int)a.n_units) {  // every unit of this rank has been published
-                hdr[16] = 0u;
-                __threadfence_system();
-                for (int pr = 0; pr < a.world; pr++) atomicAdd_system(reinterpret_cast<unsigned int*>(a.peers[pr]), 1u);
-            }
-            // every publishing CTA waits for all ranks' arrivals, then merges its share of the output (fa_reduce algebra)
-            s_flag[3] = xchg_wait_arrivals(hdr, sp_step * (unsigned int)a.world) ? 1 : 0;
-        }
-        bar_consumers();
-        if (s_flag[3] == 0) return;  // timed out (error flag raised in the header): no merge, no step count; the kernel ends normally
         const int64_t n_out = p.total_rows * D;
-        const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;  // share ~ units published
-        const float* part = reinterpret_cast<const float*>(a.peers[a.rank] + kXchgHeader) + sp_n_floats + sp_gen_off;
-        for (int64_t idx = lo + threadIdx.x; idx < hi; idx += CW * 32) {
-            const int64_t row = idx / D;
-            const int d = (int)(idx % D);
-            float M = -INFINITY;
-            for (int s2 = 0; s2 < a.world; s2++) M = fmaxf(M, __ldcv(part + ((int64_t)s2 * p.total_rows + row) * (D + 2) + D));
-            const float Mu = (M == -INFINITY) ? 0.f : M;
-            float L = 0.f, acc = 0.f;
-            for (int s2 = 0; s2 < a.world; s2++) {
-                const float* rec = part + ((int64_t)s2 * p.total_rows + row) * (D + 2);
-                const float wt = __expf(__ldcv(rec + D) - Mu);
-                L += __ldcv(rec + D + 1) * wt;
-                acc += __ldcv(rec + d) * wt;
+        const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;
+        const uint2* part = reinterpret_cast<const uint2*>(a.peers[a.rank] + sp_ll_off) + (int64_t)(sp_step & 1u) * a.world * sp_n_floats;
+        // ---- wait until every element this CTA will read carries this step's tag (bounded; a missing rank raises the error flag) ----
+        {
+            const unsigned int ms = hdr[kXchgTimeoutWord] ? hdr[kXchgTimeoutWord] : kXchgDefaultTimeoutMs;
+            const unsigned long long t0 = xchg_now_ns(), limit = (unsigned long long)ms * 1000000ull;
+            bool ok = true;
+            for (int64_t idx = lo + threadIdx.x; idx < hi && ok; idx += CW * 32) {
+                const int64_t row = idx / D;
+                const int d = (int)(idx % D);
+                for (int s2 = 0; s2 < a.world && ok; s2++) {
+                    const uint2* rec = part + ((int64_t)s2 * p.total_rows + row) * (D + 2);
+                    unsigned int spins = 0;
+                    while (ld_ll(rec + d).y != sp_tag || ld_ll(rec + D).y != sp_tag || ld_ll(rec + D + 1).y != sp_tag) {
+                        if ((++spins & 63u) == 0 && xchg_now_ns() - t0 > limit) { ok = false; break; }
+                    }
+                }
             }
-            const float y = L > 0.f ? acc / L : 0.f;
-            if (a.fdst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(a.fdst)[row * D + d] = __float2half_rn(y);
-            else reinterpret_cast<float*>(a.fdst)[row * D + d] = y;
+            if (!ok) { atomicExch(hdr + kXchgErrWord, 1u); s_flag[3] = 0; }
+        }
+        bar_consumers();
+        if (s_flag[3] != 0) {  // (timed out: no merge, the step is not counted; the kernel ends normally)
+            for (int64_t idx = lo + threadIdx.x; idx < hi; idx += CW * 32) {
+                const int64_t row = idx / D;
+                const int d = (int)(idx % D);
+                float M = -INFINITY;
+                for (int s2 = 0; s2 < a.world; s2++) M = fmaxf(M, __uint_as_float(ld_ll(part + ((int64_t)s2 * p.total_rows + row) * (D + 2) + D).x));
+                const float Mu = (M == -INFINITY) ? 0.f : M;
+                float L = 0.f, acc = 0.f;
+                for (int s2 = 0; s2 < a.world; s2++) {
+                    const uint2* rec = part + ((int64_t)s2 * p.total_rows + row) * (D + 2);
+                    const float wt = __expf(__uint_as_float(ld_ll(rec + D).x) - Mu);
+                    L += __uint_as_float(ld_ll(rec + D + 1).x) * wt;
+                    acc += __uint_as_float(ld_ll(rec + d).x) * wt;
+                }
+                const float y = L > 0.f ? acc / L : 0.f;
+                if (a.fdst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(a.fdst)[row * D + d] = __float2half_rn(y);
+                else reinterpret_cast<float*>(a.fdst)[row * D + d] = y;
+            }
         }
         bar_consumers();
         if (threadIdx.x == 0) {
+            const bool good = s_flag[3] != 0;
             const unsigned int done = atomicAdd(hdr + 17, (unsigned int)units_done);
-            if (done + (unsigned int)units_done == (unsigned int)a.n_units) { hdr[17] = 0u; hdr[32] = sp_step; }  // the step is complete on this rank
+            if (!good) hdr[18] = 1u;   // some CTA of this step timed out: the step must not be counted
+            if (done + (unsigned int)units_done == (unsigned int)a.n_units) {
+                __threadfence();
+                const bool step_ok = good && *reinterpret_cast<volatile unsigned int*>(hdr + 18) == 0u;
+                hdr[16] = 0u; hdr[17] = 0u; hdr[18] = 0u;
+                if (step_ok) hdr[32] = sp_step;  // the step is complete on this rank
+            }
         }
     };
 

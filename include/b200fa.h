@@ -211,6 +211,8 @@ int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, in
  * (a kernel that waits for a peer launched behind it never sees it arrive; B200_PROFILING.md) — emulate them with the plain
  * b200fa_flash_attn_partial + b200fa_merge_partials pair instead.
  * Two generations of the gathered area (step parity) make it safe for a fast rank to start the next step early.
+ * b200fa_flash_attn_seqpar (the fused one-kernel step, below) uses a second, flag-in-data gathered area of the same buffer: every
+ * float travels as one 8-byte store {value, tag of the step} and readers poll the elements they need — no fence, no counter.
  */
 size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D);
 int b200fa_flash_attn_partial_scatter(
