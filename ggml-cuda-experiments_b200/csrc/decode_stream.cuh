@@ -826,7 +826,10 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
         const int64_t n_out = p.total_rows * D;
         const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;
         const uint2* part = reinterpret_cast<const uint2*>(a.peers[a.rank] + sp_ll_off) + (int64_t)(sp_step & 1u) * a.world * sp_n_floats;
-        // ---- wait until every element this CTA will read carries this step's tag (bounded; a missing rank raises the error flag) ----
+        // ---- merge this CTA's share (fa_reduce algebra), polling as it goes: for eight ranks at a time ALL of an output element's
+        //      loads (its O~ value, m and l of every rank) are issued before any tag is looked at, so a poll costs one L2 round trip,
+        //      not twenty-four dependent ones (the first version polled element by element: ~20 us at 8 ranks).  Bounded: a rank that
+        //      never shows up raises the exchange's error flag; the step is then not counted (rows already merged stay written).
         {
             const unsigned int ms = hdr[kXchgTimeoutWord] ? hdr[kXchgTimeoutWord] : kXchgDefaultTimeoutMs;
             const unsigned long long t0 = xchg_now_ns(), limit = (unsigned long long)ms * 1000000ull;
@@ -834,35 +837,45 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
             for (int64_t idx = lo + threadIdx.x; idx < hi && ok; idx += CW * 32) {
                 const int64_t row = idx / D;
                 const int d = (int)(idx % D);
-                for (int s2 = 0; s2 < a.world && ok; s2++) {
-                    const uint2* rec = part + ((int64_t)s2 * p.total_rows + row) * (D + 2);
+                float M = -INFINITY, L = 0.f, acc = 0.f;
+                for (int s0 = 0; s0 < a.world && ok; s0 += 8) {
+                    uint2 vd[8], vm[8], vl[8];
                     unsigned int spins = 0;
-                    while (ld_ll(rec + d).y != sp_tag || ld_ll(rec + D).y != sp_tag || ld_ll(rec + D + 1).y != sp_tag) {
-                        if ((++spins & 63u) == 0 && xchg_now_ns() - t0 > limit) { ok = false; break; }
+                    for (;;) {
+                        bool all = true;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            if (s0 + j < a.world) {
+                                const uint2* rec = part + ((int64_t)(s0 + j) * p.total_rows + row) * (D + 2);
+                                vd[j] = ld_ll(rec + d); vm[j] = ld_ll(rec + D); vl[j] = ld_ll(rec + D + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            if (s0 + j < a.world) all = all && vd[j].y == sp_tag && vm[j].y == sp_tag && vl[j].y == sp_tag;
+                        if (all) break;
+                        if ((++spins & 15u) == 0 && xchg_now_ns() - t0 > limit) { ok = false; break; }
+                    }
+                    if (!ok) break;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (s0 + j < a.world) {
+                            const float mj = __uint_as_float(vm[j].x);
+                            const float Mn = fmaxf(M, mj);
+                            const float Mu = (Mn == -INFINITY) ? 0.f : Mn;
+                            const float w_old = __expf(M - Mu), w_new = __expf(mj - Mu);   // exp(-inf) = 0 for empty partials
+                            L = L * w_old + __uint_as_float(vl[j].x) * w_new;
+                            acc = acc * w_old + __uint_as_float(vd[j].x) * w_new;
+                            M = Mn;
+                        }
                     }
                 }
-            }
-            if (!ok) { atomicExch(hdr + kXchgErrWord, 1u); s_flag[3] = 0; }
-        }
-        bar_consumers();
-        if (s_flag[3] != 0) {  // (timed out: no merge, the step is not counted; the kernel ends normally)
-            for (int64_t idx = lo + threadIdx.x; idx < hi; idx += CW * 32) {
-                const int64_t row = idx / D;
-                const int d = (int)(idx % D);
-                float M = -INFINITY;
-                for (int s2 = 0; s2 < a.world; s2++) M = fmaxf(M, __uint_as_float(ld_ll(part + ((int64_t)s2 * p.total_rows + row) * (D + 2) + D).x));
-                const float Mu = (M == -INFINITY) ? 0.f : M;
-                float L = 0.f, acc = 0.f;
-                for (int s2 = 0; s2 < a.world; s2++) {
-                    const uint2* rec = part + ((int64_t)s2 * p.total_rows + row) * (D + 2);
-                    const float wt = __expf(__uint_as_float(ld_ll(rec + D).x) - Mu);
-                    L += __uint_as_float(ld_ll(rec + D + 1).x) * wt;
-                    acc += __uint_as_float(ld_ll(rec + d).x) * wt;
-                }
+                if (!ok) break;
                 const float y = L > 0.f ? acc / L : 0.f;
                 if (a.fdst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(a.fdst)[row * D + d] = __float2half_rn(y);
                 else reinterpret_cast<float*>(a.fdst)[row * D + d] = y;
             }
+            if (!ok) { atomicExch(hdr + kXchgErrWord, 1u); s_flag[3] = 0; }
         }
         bar_consumers();
         if (threadIdx.x == 0) {

@@ -213,6 +213,7 @@ int b200fa_merge_partials(const float* partials, int n_parts, int64_t n_rows, in
  * Two generations of the gathered area (step parity) make it safe for a fast rank to start the next step early.
  * b200fa_flash_attn_seqpar (the fused one-kernel step, below) uses a second, flag-in-data gathered area of the same buffer: every
  * float travels as one 8-byte store {value, tag of the step} and readers poll the elements they need — no fence, no counter.
+ * (On a timeout of the fused step the rows merged before the missing rank was given up on stay written; the step is not counted.)
  */
 size_t b200fa_xchg_bytes(int world, int64_t n_rows, int64_t D);
 int b200fa_flash_attn_partial_scatter(
