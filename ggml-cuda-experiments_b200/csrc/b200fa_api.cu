@@ -336,14 +336,14 @@ int launch_combine(const float* part, int n_parts, int64_t rows, void* dst, int 
     return cudaGetLastError() == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
-template <int D, int KV, int RH, bool EXT, bool T8 = false>
+template <int D, int KV, int RH, bool EXT, bool T8 = false, bool SP = false>
 int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t st) {
     constexpr int smem = dk_smem_bytes<D, KV == B200FA_TYPE_Q8_0, RH, T8>();
     static thread_local bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT, T8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
+        if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT, T8, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return B200FA_ERR_CUDA;
         attr_set[dev] = true;
     }
     // Programmatic dependent launch: this kernel may be scheduled while the previous kernel of the stream drains (it waits in-kernel,
@@ -358,7 +358,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         int& mc = max_clusters[dev >= 0 && dev < 64 ? dev : 0][args.cluster_k];
         if (mc == 0) {
             mc = -1;
-            if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT, T8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            if (cudaFuncSetAttribute(fa_decode_stream<D, KV, RH, EXT, T8, SP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
                 cudaLaunchConfig_t qc{};
                 qc.gridDim = dim3(args.cluster_k); qc.blockDim = dim3(dk_threads<T8>()); qc.dynamicSmemBytes = smem;
                 cudaLaunchAttribute qa[1];
@@ -366,7 +366,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
                 qa[0].val.clusterDim.x = args.cluster_k; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
                 qc.attrs = qa; qc.numAttrs = 1;
                 int n = 0;
-                if (cudaOccupancyMaxActiveClusters(&n, fa_decode_stream<D, KV, RH, EXT, T8>, &qc) == cudaSuccess && n > 0) mc = n;
+                if (cudaOccupancyMaxActiveClusters(&n, fa_decode_stream<D, KV, RH, EXT, T8, SP>, &qc) == cudaSuccess && n > 0) mc = n;
             }
             (void)cudaGetLastError();
         }
@@ -387,7 +387,7 @@ int launch_stream_t(const FaParams& p, const DkArgs& a, int grid, const CUtensor
         na++;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT, T8>, p, args, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, fa_decode_stream<D, KV, RH, EXT, T8, SP>, p, args, tk, tv) == cudaSuccess ? B200FA_OK : B200FA_ERR_CUDA;
 }
 
 int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
@@ -425,9 +425,13 @@ int run_stream(const FaParams& p, const Plan& pl, char* ws, cudaStream_t st) {
     const bool small = (int64_t)p.n_q * p.gqa <= 8 && force_rh != 2;
     g_last_launches++;
     const bool ext = p.cap_in != 0.f || p.alibi_nhl2 != 0 || p.m_ne2 * p.m_ne3 > 1;
-#define B200FA_STREAM_E(DD, KK, EE) (small ? launch_stream_t<DD, KK, 1, EE>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2, EE>(p, a, pl.grid, tk, tv, st))
-#define B200FA_STREAM(DD, KK) (ext ? B200FA_STREAM_E(DD, KK, true) : B200FA_STREAM_E(DD, KK, false))
-#define B200FA_STREAM_T8(DD) (ext ? launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, true, true>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, false, true>(p, a, pl.grid, tk, tv, st))
+    // the fused sequence-parallel step has its own instantiations (SP; the entry takes no score modifiers)
+    const bool sp = a.peers != nullptr;
+    if (sp && ext) return B200FA_ERR_UNSUPPORTED;
+#define B200FA_STREAM_E(DD, KK, EE, SS) (small ? launch_stream_t<DD, KK, 1, EE, false, SS>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, KK, 2, EE, false, SS>(p, a, pl.grid, tk, tv, st))
+#define B200FA_STREAM(DD, KK) (sp ? B200FA_STREAM_E(DD, KK, false, true) : (ext ? B200FA_STREAM_E(DD, KK, true, false) : B200FA_STREAM_E(DD, KK, false, false)))
+#define B200FA_STREAM_T8(DD) (sp ? launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, false, true, true>(p, a, pl.grid, tk, tv, st) \
+                                 : (ext ? launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, true, true>(p, a, pl.grid, tk, tv, st) : launch_stream_t<DD, B200FA_TYPE_Q8_0, 1, false, true>(p, a, pl.grid, tk, tv, st)))
     // q8_0 units of at most 8 rows: the transposed tile (decode_stream.cuh, T8)
     static const bool q8_rowmajor = tune_env("B200FA_Q8_ROWMAJOR") != nullptr;
     if (q8 && small && !q8_rowmajor) return p.D == 128 ? B200FA_STREAM_T8(128) : B200FA_STREAM_T8(64);

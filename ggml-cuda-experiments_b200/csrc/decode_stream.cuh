@@ -194,7 +194,82 @@ constexpr long long DK_MAX_TOTAL_X_GRID = 0x7fffffffLL;
 // T8: the transposed q8_0 tile for units of at most 8 rows (S^T = K Q^T, O^T += V^T P'^T: the quantised rows are the A operands,
 // N = 8 covers all live rows, half the MMAs and half the accumulator registers of the row-major tile; see the T8 block below and
 // tests/test_q8t_layout.py, which restates its register algebra lane by lane on the CPU).
-template <int D, int KV_TYPE, int RH, bool EXT = false, bool T8 = false>
+// One float of a unit's triple (and, with_ml, the row's m and l) to every rank's flag-in-data area: 8-byte stores {value, tag},
+// over NVLink for the peers.  Out of line and stateless (step, tag and offsets are re-derived from the exchange header on every
+// call): the fused step's bookkeeping must not live in registers across the stream loop of the 128-register q8_0 kernel.
+template <int D>
+__device__ __noinline__ void xchg_ll_emit(char* const* peers, int rank, int world, int64_t n_floats, int64_t orow, int d, float acc,
+                                          bool with_ml, float m_nat, float l_sum) {
+    const unsigned int* hdr = reinterpret_cast<const unsigned int*>(peers[rank]);
+    const unsigned int step = hdr[32] + 1;   // this rank's step in progress (see decode_mma.cuh)
+    const unsigned int tag = xchg_ll_tag(hdr, step);
+    const int64_t ll_off = xchg_ll_offset(world, n_floats);
+    const int64_t off = ((int64_t)(step & 1u) * world + rank) * n_floats + orow * (D + 2);
+    for (int pr = 0; pr < world; pr++) {
+        uint2* out = reinterpret_cast<uint2*>(peers[pr] + ll_off) + off;
+        st_ll(out + d, acc, tag);
+        if (with_ml) { st_ll(out + D, m_nat, tag); st_ll(out + D + 1, l_sum, tag); }
+    }
+}
+
+// The merge of a share [lo, hi) of the output elements from the flag-in-data area `part` ([rank][row][D + 2] x {value, tag}): for
+// eight ranks at a time ALL of an output element's loads (its O~ value, m and l of every rank) are issued before any tag is looked
+// at, so a poll costs one L2 round trip, not twenty-four dependent ones (polling element by element: ~20 us at 8 ranks).  Bounded:
+// a rank that never shows up raises the exchange's error flag and false is returned (rows already merged stay written).
+template <int D>
+__device__ __noinline__ bool xchg_ll_merge_share(const uint2* part, int world, int64_t total_rows, int64_t lo, int64_t hi, unsigned int tag,
+                                                 void* fdst, int fdst_type, unsigned int* hdr, int n_threads) {
+    const unsigned int ms = hdr[kXchgTimeoutWord] ? hdr[kXchgTimeoutWord] : kXchgDefaultTimeoutMs;
+    const unsigned long long t0 = xchg_now_ns(), limit = (unsigned long long)ms * 1000000ull;
+    bool ok = true;
+    for (int64_t idx = lo + threadIdx.x; idx < hi && ok; idx += n_threads) {
+        const int64_t row = idx / D;
+        const int d = (int)(idx % D);
+        float M = -INFINITY, L = 0.f, acc = 0.f;
+        for (int s0 = 0; s0 < world && ok; s0 += 8) {
+            uint2 vd[8], vm[8], vl[8];
+            unsigned int spins = 0;
+            for (;;) {
+                bool all = true;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (s0 + j < world) {
+                        const uint2* rec = part + ((int64_t)(s0 + j) * total_rows + row) * (D + 2);
+                        vd[j] = ld_ll(rec + d); vm[j] = ld_ll(rec + D); vl[j] = ld_ll(rec + D + 1);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (s0 + j < world) all = all && vd[j].y == tag && vm[j].y == tag && vl[j].y == tag;
+                if (all) break;
+                if ((++spins & 15u) == 0 && xchg_now_ns() - t0 > limit) { ok = false; break; }
+            }
+            if (!ok) break;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (s0 + j < world) {
+                    const float mj = __uint_as_float(vm[j].x);
+                    const float Mn = fmaxf(M, mj);
+                    const float Mu = (Mn == -INFINITY) ? 0.f : Mn;
+                    const float w_old = __expf(M - Mu), w_new = __expf(mj - Mu);   // exp(-inf) = 0 for empty partials
+                    L = L * w_old + __uint_as_float(vl[j].x) * w_new;
+                    acc = acc * w_old + __uint_as_float(vd[j].x) * w_new;
+                    M = Mn;
+                }
+            }
+        }
+        if (!ok) break;
+        const float y = L > 0.f ? acc / L : 0.f;
+        if (fdst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(fdst)[row * D + d] = __float2half_rn(y);
+        else reinterpret_cast<float*>(fdst)[row * D + d] = y;
+    }
+    if (!ok) atomicExch(hdr + kXchgErrWord, 1u);
+    return ok;
+}
+
+// SP: the fused sequence-parallel step (b200fa_flash_attn_seqpar).  Its own instantiation: even as a cold, out-of-line path the
+// exchange code cost the plain kernel 1-4 % (C5 51.8 -> 53.8 us inlined, 52.9 out of line), so the plain entry points carry none of it.
+template <int D, int KV_TYPE, int RH, bool EXT = false, bool T8 = false, bool SP = false>
 __global__ void __launch_bounds__(dk_threads<T8>(), 1)
 fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkArgs a,
                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV) {
@@ -795,88 +870,29 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
     DK_TL(threadIdx.x == 0, blockIdx.x * 8 + 0, dk_now());
 
     // ---- fused sequence-parallel step: where the unit triples go, and what the last CTA of the rank does ----
-    int units_done = 0;  // units whose final triple this CTA has written
-    unsigned int sp_step = 0;
-    const int64_t sp_n_floats = p.total_rows * (D + 2);
-    if (a.peers != nullptr) sp_step = reinterpret_cast<const unsigned int*>(a.peers[a.rank])[32] + 1;  // this rank's step in progress (see decode_mma.cuh)
     // Flag-in-data exchange: every float of a unit's triple goes to every rank as one 8-byte store {value, tag of this step} into
     // the rank's flag-in-data area (decode_mma.cuh); nothing is fenced and nothing is counted.  A reader polls the elements it
     // needs until their tags match, which is all the synchronisation there is: one NVLink traversal between the last local
     // chunk and the merge instead of stores + system fence + counter increment + counter poll.
-    unsigned int sp_tag = 0;
-    int64_t sp_ll_off = 0;
-    if (a.peers != nullptr) {
-        sp_tag = xchg_ll_tag(reinterpret_cast<const unsigned int*>(a.peers[a.rank]), sp_step);
-        sp_ll_off = xchg_ll_offset(a.world, sp_n_floats);
-    }
+    int units_done = 0;  // units whose final triple this CTA has written
+    const int64_t sp_n_floats = p.total_rows * (D + 2);
     auto emit_triple = [&](int64_t orow, int d, float acc, bool with_ml, float m_nat, float l_sum) {
-        const int64_t off = ((int64_t)(sp_step & 1u) * a.world + a.rank) * sp_n_floats + orow * (D + 2);
-        for (int pr = 0; pr < a.world; pr++) {  // over NVLink for the peers
-            uint2* out = reinterpret_cast<uint2*>(a.peers[pr] + sp_ll_off) + off;
-            st_ll(out + d, acc, sp_tag);
-            if (with_ml) { st_ll(out + D, m_nat, sp_tag); st_ll(out + D + 1, l_sum, sp_tag); }
-        }
+        xchg_ll_emit<D>(a.peers, a.rank, a.world, sp_n_floats, orow, d, acc, with_ml, m_nat, l_sum);
     };
     auto finish_seqpar = [&]() {
-        if (a.peers == nullptr || units_done == 0) return;  // (uniform per CTA) only CTAs that published a unit have anything to do
+        if (!SP || a.peers == nullptr || units_done == 0) return;  // (uniform per CTA) only CTAs that published a unit have anything to do
         unsigned int* hdr = reinterpret_cast<unsigned int*>(a.peers[a.rank]);
+        const unsigned int sp_step = hdr[32] + 1;   // this rank's step in progress
+        const unsigned int sp_tag = xchg_ll_tag(hdr, sp_step);
+        const int64_t sp_ll_off = xchg_ll_offset(a.world, sp_n_floats);
         if (threadIdx.x == 0) s_flag[2] = (int)atomicAdd(hdr + 16, (unsigned int)units_done);   // this CTA's share of the merge ~ units published
         if (threadIdx.x == 0) s_flag[3] = 1;
         bar_consumers();
         const int64_t n_out = p.total_rows * D;
         const int64_t lo = n_out * s_flag[2] / a.n_units, hi = n_out * (s_flag[2] + units_done) / a.n_units;
         const uint2* part = reinterpret_cast<const uint2*>(a.peers[a.rank] + sp_ll_off) + (int64_t)(sp_step & 1u) * a.world * sp_n_floats;
-        // ---- merge this CTA's share (fa_reduce algebra), polling as it goes: for eight ranks at a time ALL of an output element's
-        //      loads (its O~ value, m and l of every rank) are issued before any tag is looked at, so a poll costs one L2 round trip,
-        //      not twenty-four dependent ones (the first version polled element by element: ~20 us at 8 ranks).  Bounded: a rank that
-        //      never shows up raises the exchange's error flag; the step is then not counted (rows already merged stay written).
-        {
-            const unsigned int ms = hdr[kXchgTimeoutWord] ? hdr[kXchgTimeoutWord] : kXchgDefaultTimeoutMs;
-            const unsigned long long t0 = xchg_now_ns(), limit = (unsigned long long)ms * 1000000ull;
-            bool ok = true;
-            for (int64_t idx = lo + threadIdx.x; idx < hi && ok; idx += CW * 32) {
-                const int64_t row = idx / D;
-                const int d = (int)(idx % D);
-                float M = -INFINITY, L = 0.f, acc = 0.f;
-                for (int s0 = 0; s0 < a.world && ok; s0 += 8) {
-                    uint2 vd[8], vm[8], vl[8];
-                    unsigned int spins = 0;
-                    for (;;) {
-                        bool all = true;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            if (s0 + j < a.world) {
-                                const uint2* rec = part + ((int64_t)(s0 + j) * p.total_rows + row) * (D + 2);
-                                vd[j] = ld_ll(rec + d); vm[j] = ld_ll(rec + D); vl[j] = ld_ll(rec + D + 1);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            if (s0 + j < a.world) all = all && vd[j].y == sp_tag && vm[j].y == sp_tag && vl[j].y == sp_tag;
-                        if (all) break;
-                        if ((++spins & 15u) == 0 && xchg_now_ns() - t0 > limit) { ok = false; break; }
-                    }
-                    if (!ok) break;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        if (s0 + j < a.world) {
-                            const float mj = __uint_as_float(vm[j].x);
-                            const float Mn = fmaxf(M, mj);
-                            const float Mu = (Mn == -INFINITY) ? 0.f : Mn;
-                            const float w_old = __expf(M - Mu), w_new = __expf(mj - Mu);   // exp(-inf) = 0 for empty partials
-                            L = L * w_old + __uint_as_float(vl[j].x) * w_new;
-                            acc = acc * w_old + __uint_as_float(vd[j].x) * w_new;
-                            M = Mn;
-                        }
-                    }
-                }
-                if (!ok) break;
-                const float y = L > 0.f ? acc / L : 0.f;
-                if (a.fdst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(a.fdst)[row * D + d] = __float2half_rn(y);
-                else reinterpret_cast<float*>(a.fdst)[row * D + d] = y;
-            }
-            if (!ok) { atomicExch(hdr + kXchgErrWord, 1u); s_flag[3] = 0; }
-        }
+        // ---- merge this CTA's share (fa_reduce algebra), polling as it goes (out of line: the cold path must not cost the stream loop registers) ----
+        if (!xchg_ll_merge_share<D>(part, a.world, p.total_rows, lo, hi, sp_tag, a.fdst, a.fdst_type, hdr, CW * 32)) s_flag[3] = 0;
         bar_consumers();
         if (threadIdx.x == 0) {
             const bool good = s_flag[3] != 0;
@@ -1112,7 +1128,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                         if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
                         else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
                     }
-                } else if (a.peers != nullptr) {
+                } else if (SP && a.peers != nullptr) {
                     emit_triple(orow, d, acc, first, M * kLn2, L);
                 } else {
                     float* out = p.part_out + orow * (D + 2);
@@ -1166,7 +1182,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                     if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
                     else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
                 }
-            } else if (a.peers != nullptr) {
+            } else if (SP && a.peers != nullptr) {
                 emit_triple(orow, d, acc, d == 0, M * kLn2, L);
             } else {
                 float* out = p.part_out + orow * (D + 2);
@@ -1288,7 +1304,7 @@ fa_decode_stream(const __grid_constant__ FaParams p, const __grid_constant__ DkA
                         if (p.dst_type == B200FA_TYPE_F16) reinterpret_cast<__half*>(p.dst)[orow * p.Dr + d] = __float2half_rn(y);
                         else reinterpret_cast<float*>(p.dst)[orow * p.Dr + d] = y;
                     }
-                } else if (a.peers != nullptr) {
+                } else if (SP && a.peers != nullptr) {
                     emit_triple(orow, d, acc, d == 0, M * kLn2, L);
                 } else {
                     float* out = p.part_out + orow * (D + 2);

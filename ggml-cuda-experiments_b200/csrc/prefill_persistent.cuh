@@ -259,6 +259,11 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may take over SMs as this grid's CTAs retire
+    // diagnostics (tuning builds only: a.dump is null otherwise): per CTA %globaltimer at entry / after the dependency wait / at exit and
+    // the clock64 cycles between the last two — cycles / ns is the SM clock the kernel really ran at (~1.65 GHz on C3)
+    long long* ct = (a.dump != nullptr && threadIdx.x == 0) ? reinterpret_cast<long long*>(a.dump) + 2 * 32 * 8 + blockIdx.x * 4 : nullptr;
+    auto gtime = [] { long long x; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x)); return x; };
+    if (ct) ct[0] = gtime();
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
             mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1);
@@ -281,6 +286,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     // Programmatic dependent launch (see launch_prefill_persistent): everything above ran while the previous kernel of the stream
     // was still draining; nothing below touches global memory before that kernel has completed and flushed.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (ct) { ct[1] = gtime(); ct[3] = clock64(); }
 
     // work index -> (first 128-row tile, head, batch); heavy (late) tile pairs first
     auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w / pa.n_seg, qt0, iq2, iq3); };
@@ -537,6 +543,7 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     if (warp < 8 && lane == 0) bulk_wait_all0();  // this lane's output boxes have been written
     tc_fence_before();
     __syncthreads();
+    if (ct) { ct[2] = gtime(); ct[3] = clock64() - ct[3]; }
     if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem, PF_TMEM_COLS);

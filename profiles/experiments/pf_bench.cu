@@ -103,41 +103,31 @@ int main(int argc, char** argv) {
         printf("parity vs shipped library: max_abs=%.3e (max |ref| %.3f) out-of-tolerance=%zu of %zu\n", mx, mref, bad, nq_el);
     }
 #ifdef B200FA_TUNING
-    if (getenv("PF_DUMP_CTA")) {  // per-item clock64 stamps of one CTA (softmax groups + epilogue warp 12)
-        float* dump; CK(cudaMalloc(&dump, 32768)); 
-        for (int rep = 0; rep < 2; rep++) {
-            CK(cudaMemset(dump, 0, 32768));
-            pf_debug().dump = dump; pf_debug().dump_cta = atoi(getenv("PF_DUMP_CTA"));
-            run(0); CK(cudaStreamSynchronize(st));
+    if (getenv("PF_DUMP_CTA")) {  // clock64 / %globaltimer stamps (tuning build: -DB200FA_TUNING): per-item timeline of one CTA, per-CTA entry / exit
+        const size_t dump_bytes = 2 * 32 * 8 * 8 + 160 * 4 * 8;
+        float* dump; CK(cudaMalloc(&dump, dump_bytes));
+        pf_debug().dump = dump; pf_debug().dump_cta = atoi(getenv("PF_DUMP_CTA"));
+        CK(cudaMemset(dump, 0, dump_bytes));
+        run(0); CK(cudaStreamSynchronize(st)); run(0); CK(cudaStreamSynchronize(st));   // the second (warm) run's stamps stay
+        long long h[2][32][8]; CK(cudaMemcpy(h, dump, sizeof(h), cudaMemcpyDeviceToHost));
+        const long long t0 = h[0][0][0] && h[0][0][0] < h[1][0][0] ? h[0][0][0] : h[1][0][0];
+        for (int t = 0; t < 2; t++) {
+            printf("tile %d: item | work | halves | start | loop end | O read out | stored   (cycles since the CTA's first item)\n", t);
+            for (int k = 0; k < 32 && h[t][k][0]; k++)
+                printf("   %2d | %5lld | %3lld | %7lld | %7lld | %7lld | %7lld | %5.0f per half (incl. the wait for the item's first scores)\n", k, h[t][k][4], h[t][k][5], h[t][k][0] - t0, h[t][k][1] - t0,
+                       h[t][k][2] - t0, h[t][k][3] - t0, h[t][k][5] ? (double)(h[t][k][1] - h[t][k][0]) / h[t][k][5] : 0.0);
         }
         // back-to-back launches as in the timed loop: CTA entry / dependency wait / exit of the LAST launch (%globaltimer, ns)
         for (int i = 0; i < 6; i++) run(i % nsets);
         CK(cudaStreamSynchronize(st));
-        {
-            long long c[160][8]; CK(cudaMemcpy(c, (char*)dump + 5 * 32 * 8 * 8, sizeof(c), cudaMemcpyDeviceToHost));
-            const int G = prop.multiProcessorCount < 160 ? prop.multiProcessorCount : 160;
-            long long e0 = c[0][0], w0 = 0, x0 = c[0][2], x1 = 0, e1 = 0;
-            for (int i = 0; i < G; i++) { if (c[i][0] < e0) e0 = c[i][0]; if (c[i][0] > e1) e1 = c[i][0]; if (c[i][1] > w0) w0 = c[i][1]; if (c[i][2] < x0) x0 = c[i][2]; if (c[i][2] > x1) x1 = c[i][2]; }
-            printf("last of 6 back-to-back launches (ns after the first CTA entry): last entry %lld | dependency wait over %lld | first exit %lld | last exit %lld\n", e1 - e0, w0 - e0, x0 - e0, x1 - e0);
-            printf("  CTA 0: %lld cycles in %lld ns between the dependency wait and the exit -> %.0f MHz\n", c[0][3], c[0][2] - c[0][1], 1e3 * c[0][3] / (double)(c[0][2] - c[0][1]));
-            printf("  per CTA: exit us after the dependency wait / items / half tiles of tile 1 / first two work indices\n");
-            for (int i = 0; i < G; i++) printf("%s%5.1f/%lld/%lld/%lld,%lld", i % 8 ? "  " : "\n    ", (c[i][2] - w0) * 1e-3, c[i][4], c[i][5], c[i][6], c[i][4] > 1 ? c[i][7] : -1LL); printf("\n");
-        }
+        long long c[160][4]; CK(cudaMemcpy(c, (char*)dump + 2 * 32 * 8 * 8, sizeof(c), cudaMemcpyDeviceToHost));
+        const int G = prop.multiProcessorCount < 160 ? prop.multiProcessorCount : 160;
+        long long e0 = c[0][0], w0 = 0, x0 = c[0][2], x1 = 0, e1 = 0;
+        for (int i = 0; i < G; i++) { if (c[i][0] < e0) e0 = c[i][0]; if (c[i][0] > e1) e1 = c[i][0]; if (c[i][1] > w0) w0 = c[i][1]; if (c[i][2] < x0) x0 = c[i][2]; if (c[i][2] > x1) x1 = c[i][2]; }
+        printf("last of 6 back-to-back launches (ns after the first CTA entry): last entry %lld | dependency wait over %lld | first exit %lld | last exit %lld\n", e1 - e0, w0 - e0, x0 - e0, x1 - e0);
+        printf("  CTA 0: %lld cycles in %lld ns between the dependency wait and the exit -> %.0f MHz\n", c[0][3], c[0][2] - c[0][1], 1e3 * c[0][3] / (double)(c[0][2] - c[0][1]));
+        printf("  exits by CTA (us after the dependency wait):"); for (int i = 0; i < G; i++) printf("%s%.1f", i % 16 ? " " : "\n    ", (c[i][2] - w0) * 1e-3); printf("\n");
         pf_debug().dump = nullptr;
-        long long h[5][32][8]; CK(cudaMemcpy(h, dump, sizeof(h), cudaMemcpyDeviceToHost));
-        long long t0 = h[0][0][0] && h[0][0][0] < h[1][0][0] ? h[0][0][0] : h[1][0][0];
-        for (int t = 0; t < 2; t++) {
-            printf("tile %d: item | work | halves | start | first S | loop end | O read out | stored   (cycles since the CTA's first item)\n", t);
-            for (int k = 0; k < 32 && h[t][k][0]; k++)
-                printf("   %2d | %5lld | %3lld | %7lld | %7lld | %7lld | %7lld | %7lld | %5.0f per half\n", k, h[t][k][4], h[t][k][5], h[t][k][0] - t0, h[t][k][6] - t0, h[t][k][1] - t0,
-                       h[t][k][2] - t0, h[t][k][3] - t0, h[t][k][5] ? (double)(h[t][k][1] - h[t][k][6]) / h[t][k][5] : 0.0);
-        }
-        printf("producer: item | published | Q0 issued | Q1 issued | first K slot free | last V issued\n");
-        for (int k = 0; k < 32 && h[2][k][0]; k++) printf("   %2d | %7lld | %7lld | %7lld | %7lld | %7lld\n", k, h[2][k][0] - t0, h[2][k][1] - t0, h[2][k][2] - t0, h[2][k][3] - t0, h[2][k][4] - t0);
-        for (int t = 0; t < 2; t++) {
-            printf("issuer %d: item | item seen | first K full | Q full | item done\n", t);
-            for (int k = 0; k < 32 && h[3 + t][k][0]; k++) printf("   %2d | %7lld | %7lld | %7lld | %7lld\n", k, h[3 + t][k][0] - t0, h[3 + t][k][1] - t0, h[3 + t][k][2] - t0, h[3 + t][k][3] - t0);
-        }
     }
 #endif
     for (int i = 0; i < 10; i++) run(i % nsets);
