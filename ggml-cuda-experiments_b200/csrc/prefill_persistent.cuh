@@ -67,10 +67,19 @@ __device__ __forceinline__ void pp_load_q(const FaParams& p, const PfArgs& a, vo
     }
 }
 
+// PACK = false: the packing fields are compile-time constants again (pack_sh = 0, 128 positions per tile) — as run-time values they
+// lengthened the producer's serial schedule computation, which sits on the critical path between two items (C3 +0.6 us).
+template <bool PACK>
+__device__ __forceinline__ PfArgs pp_args(const PpArgs& pa) {
+    PfArgs a = pa.f;
+    if (!PACK) { a.pack_sh = 0; a.q_rows = PF_BM; }
+    return a;
+}
+template <bool PACK>
 __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs& pa, PpShared& sm, int lane, const CUtensorMap& tmQ,
                                                  const CUtensorMap& tmK, const CUtensorMap& tmV) {
     using namespace ptx;
-    const PfArgs& a = pa.f;
+    const PfArgs a = pp_args<PACK>(pa);
     auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w / pa.n_seg, qt0, iq2, iq3); };
     const bool causal = p.causal != 0 || (pa.detect_causal != 0 && __ldcg(pa.counters + 2) == 0u);
     // ===================== producer warp: hands out items, builds their schedule, streams Q / K / V =====================
@@ -140,9 +149,10 @@ __device__ __forceinline__ void pp_producer_role(const FaParams& p, const PpArgs
     }
 }
 
+template <bool PACK>
 __device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& pa, PpShared& sm, uint32_t tmem, const int t) {
     using namespace ptx;
-    const PfArgs& a = pa.f;
+    const PfArgs a = pp_args<PACK>(pa);
     auto decode_item = [&](int w, int& qt0, int& iq2, int& iq3) { pp_decode_item(p, a, w / pa.n_seg, qt0, iq2, iq3); };
     // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 query tile 1 =====================
     if (elect_one()) {
@@ -246,7 +256,7 @@ __device__ __forceinline__ void pp_issuer_role(const FaParams& p, const PpArgs& 
     }
 }
 
-template <int POLY, bool EXT = false>
+template <int POLY, bool EXT = false, bool PACK = false>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant__ PpArgs pa,
                       const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -255,13 +265,17 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t pp_smem_raw[];  // 128B-swizzled TMA tiles need 1024-byte alignment; no slack to spare
     if ((smem_u32(pp_smem_raw) & 1023u) != 0) __trap();
     PpShared& sm = *reinterpret_cast<PpShared*>(pp_smem_raw);
-    const PfArgs& a = pa.f;
+    const PfArgs a = pp_args<PACK>(pa);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may take over SMs as this grid's CTAs retire
     // diagnostics (tuning builds only: a.dump is null otherwise): per CTA %globaltimer at entry / after the dependency wait / at exit and
     // the clock64 cycles between the last two — cycles / ns is the SM clock the kernel really ran at (~1.65 GHz on C3)
+#ifdef B200FA_TUNING
     long long* ct = (a.dump != nullptr && threadIdx.x == 0) ? reinterpret_cast<long long*>(a.dump) + 2 * 32 * 8 + blockIdx.x * 4 : nullptr;
+#else
+    long long* const ct = nullptr;
+#endif
     auto gtime = [] { long long x; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x)); return x; };
     if (ct) ct[0] = gtime();
     if (threadIdx.x == 0) {
@@ -294,9 +308,9 @@ fa_prefill_persistent(const __grid_constant__ FaParams p, const __grid_constant_
     if (warp >= 8) {
         reg_dec<PF_REGS_OTHER>();
         if (warp == 8) {
-            pp_producer_role(p, pa, sm, lane, tmQ, tmK, tmV);
+            pp_producer_role<PACK>(p, pa, sm, lane, tmQ, tmK, tmV);
         } else if (warp <= 10) {
-            pp_issuer_role(p, pa, sm, tmem, warp - 9);
+            pp_issuer_role<PACK>(p, pa, sm, tmem, warp - 9);
         }
     } else {
         // ===================== softmax / correction / epilogue: thread = query row =====================
@@ -659,15 +673,16 @@ inline int launch_prefill_persistent(const FaParams& p, char* ws, size_t qf16_by
     static_assert(smem_bytes <= 227 * 1024, "prefill shared memory budget");
     static const int poly = tune_env("B200FA_POLY") ? atoi(tune_env("B200FA_POLY")) : 2;  // default: every 2nd pair on the FMA pipes
 #ifdef B200FA_TUNING
-    auto kern = ext ? fa_prefill_persistent<2, true>
+    auto kern = a.pack_sh ? fa_prefill_persistent<2, false, true>
+              : ext ? fa_prefill_persistent<2, true>
                     : (poly == 0 ? fa_prefill_persistent<0> : (poly == 3 ? fa_prefill_persistent<3> : (poly == 4 ? fa_prefill_persistent<4> : fa_prefill_persistent<2>)));
-    const int ai = ext ? 4 : (poly == 0 ? 0 : (poly == 3 ? 2 : (poly == 4 ? 3 : 1)));
+    const int ai = a.pack_sh ? 5 : ext ? 4 : (poly == 0 ? 0 : (poly == 3 ? 2 : (poly == 4 ? 3 : 1)));
 #else
-    auto kern = ext ? fa_prefill_persistent<2, true> : fa_prefill_persistent<2>;
-    const int ai = ext ? 4 : 1;
+    auto kern = a.pack_sh ? fa_prefill_persistent<2, false, true> : (ext ? fa_prefill_persistent<2, true> : fa_prefill_persistent<2>);  // (packing excludes the ext2 modifiers)
+    const int ai = a.pack_sh ? 5 : (ext ? 4 : 1);
     (void)poly;
 #endif
-    static thread_local bool attr_set[64][5] = {};
+    static thread_local bool attr_set[64][6] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev][ai]) {
