@@ -479,7 +479,7 @@ def main():
             tf = fl / (t * 1e-3) / 1e12
             out[name] = {"tflops": tf, "us_per_step": t * 1e3, "launches_per_step": nl, "dispatch": disp,
                          "roofline": {"bound": "tensor", "kernel": "fa_prefill_persistent", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                                      "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_src + " burst", "frac_of_nominal_2250": tf / 2250.0,
+                                      "frac": tf / peaks["bf16_tflops"], "traffic": ncu_traffic("c3_fa_prefill_persistent") if name == "causal_flag" else None, "peak_source": peak_src + " burst", "frac_of_nominal_2250": tf / 2250.0,
                                       "algorithmic_flops_per_launch": fl},
                          "parity": parity_block(pairs, f"all 2048 rows of heads {heads} of input set 0")}
         out["config"] = "c3: LLaMA-7B prefill, 32 heads, d=128, 2048x2048 causal f16 Q/K/V, f32 out (BASELINE.json configs[2]); causal FLOPs 34.36 G; each rank its own copy"
