@@ -230,8 +230,9 @@ int b200fa_flash_attn_partial_scatter(
     uint32_t flags, void* workspace, size_t workspace_bytes, b200fa_stream_t stream);
 int b200fa_merge_partials_wait(void* xchg, int world, int64_t n_rows, int64_t D, void* dst, int dst_type, b200fa_stream_t stream);
 /* The whole sequence-parallel step in one call — and, for decode shapes (<= 16 rows per KV head), in ONE kernel: the stream
- * decode kernel stores each unit's triple straight into every rank's exchange buffer over NVLink; the last CTA of the rank
- * signals the peers, waits for their arrivals and merges into dst [rows][D].  dst holds the same result on every rank. */
+ * decode kernel stores each unit's triple straight into every rank's exchange buffer over NVLink as {value, step tag} pairs, and
+ * the CTAs that published a unit poll the other ranks' elements of their share of the output until the tags match, then merge into
+ * dst [rows][D] (no fence, no counter, no second NVLink round trip).  dst holds the same result on every rank. */
 int b200fa_flash_attn_seqpar(
     const void* q, const void* k, const void* v, const void* mask, void* dst, float scale,
     int q_type, int kv_type, int dst_type,
