@@ -99,3 +99,13 @@ def test_workspace_size_is_deterministic_and_covers_partials():
     b = P.workspace_size(0, 1, 128, 1, 32, 1, 4096, 32, 1)
     assert a == b and a >= 32 * 130 * 4
     assert P.workspace_size(0, 1, 128, 1, 32, 1, 64, 32, 1) >= 256
+
+
+def test_exchange_buffer_layout_needs_no_gpu():
+    """b200fa_xchg_bytes: header, this rank's staged triples, two generations of gathered triples (NCCL-free three-launch path) and
+    two generations of the fused step's flag-in-data area, where every float travels as an 8-byte {value, step tag} pair."""
+    P = load_package()
+    for world, rows, D in ((1, 32, 128), (2, 32, 128), (8, 256, 64)):
+        n = rows * (D + 2)
+        assert P.PeerExchange.nbytes(world, rows, D) == 256 + (1 + 2 * world) * n * 4 + 2 * world * n * 8
+    assert P.PeerExchange.nbytes(0, 32, 128) == 0 and P.PeerExchange.nbytes(2, 0, 128) == 0
