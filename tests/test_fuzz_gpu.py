@@ -82,3 +82,35 @@ def test_random_shape_dispatch_boundaries(seed):
     flags = pkg().FLAG_CAUSAL if (c["mask_kind"] == "causal" and c["flag"]) else 0
     run_both(Q, K, V, mask, flags=flags, q_f16=c["q_f16"], dst_f16=c["dst_f16"], cache_view=c["cache_view"], q8=c["q8"],
              mask_pad=32 if c["flag"] else None, what=str(c))
+
+
+def _case3(seed):
+    """Round 2: GQA-packed tiles — every power-of-two group, query counts from one position to several packed tile pairs, KV ranges
+    long enough to be split into segments, padded head sizes, q8_0 caches, masks with and without the flag."""
+    r = np.random.RandomState(2000 + seed)
+    D = int(r.choice([128, 128, 128, 64, 80, 112]))
+    gqa = int(r.choice([2, 4, 8, 16, 32]))
+    Hk = int(r.choice([1, 2, 3])) if gqa < 32 else 1
+    H = Hk * gqa
+    B = int(r.choice([1, 1, 2]))
+    n_q = int(r.choice([1, 2, 3, 5, 8, 13, 16, 17, 31, 32, 33, 50, 64, 100, 127]))
+    if n_q * gqa <= 16:
+        n_q = 16 // gqa + 1
+    n_kv = int(r.choice([n_q + 5, 129, 640, 1000, 2048, 3000, 4500]))
+    mask_kind = str(r.choice(["none", "zeros", "noise", "causal", "causal"]))
+    if mask_kind == "causal" and n_kv < n_q:
+        mask_kind = "noise"
+    q8 = bool(r.rand() < 0.3) and D in (64, 128)
+    return dict(D=D, n_q=n_q, n_kv=n_kv, H=H, Hk=Hk, B=B, mask_kind=mask_kind, q8=q8, q_f16=bool(r.rand() < 0.4),
+                dst_f16=bool(r.rand() < 0.3), cache_view=bool(r.rand() < 0.4) and not q8, flag=bool(r.rand() < 0.5), seed=seed)
+
+
+@pytest.mark.parametrize("seed", list(range(48)))
+def test_random_shape_packed_tiles(seed):
+    c = _case3(seed)
+    Q, K, V = synth_qkv(c["D"], c["n_q"], c["n_kv"], c["H"], c["Hk"], n_batch=c["B"], seeds=(seed + 21, seed + 22, seed + 23))
+    mask = make_mask(c["mask_kind"], c["n_q"], c["n_kv"])
+    flags = pkg().FLAG_CAUSAL if (c["mask_kind"] == "causal" and c["flag"]) else 0
+    run_both(Q, K, V, mask, flags=flags, q_f16=c["q_f16"], dst_f16=c["dst_f16"], cache_view=c["cache_view"], q8=c["q8"],
+             mask_pad=32 if c["flag"] else None, what=str(c))
+    assert pkg().last_dispatch() == "prefill_tcgen05", (pkg().last_dispatch(), c)
